@@ -1,0 +1,415 @@
+// backward.cu -- visibility, per-view search radius (exact radix select), occupancy gather,
+// z-buffer and colour scatters.
+//
+// Replaces the fast branch of EllipticalRasterizer.backward (DSS/core/rasterizer.py:845-972) and
+// RasterizePointsBackwardCudaFastKernel (DSS/csrc/rasterize_points_backward.cu:30-212).  The reference
+// scatters from pixels to points with two float atomics per (pixel, point) pair after building an FRNN
+// grid with per-view host loops; here every visible point GATHERS its pixel disc -- no grid, no
+// atomics, deterministic -- which is the same sum because the grid is only an accelerator for the
+// d^2 <= r^2 test.
+#include <math_constants.h>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace dss {
+
+static inline unsigned int nblocks(int64_t items, int threads, int sm_count, int per_sm) {
+    int64_t b = (items + threads - 1) / threads;
+    const int64_t cap = (int64_t)sm_count * per_sm;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (unsigned int)b;
+}
+
+// ---------------------------------------------------------------------------------------------
+// visibility (rasterizer.py:854-860): any slot of a pixel whose first slot is occupied.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+visibility_kernel(const int32_t *__restrict__ idx, int64_t num_pixels, int K, int64_t P,
+                  uint8_t *__restrict__ visible) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < num_pixels;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t *row = idx + i * K;
+        if (row[0] < 0) continue;
+        for (int k = 0; k < K; ++k) {
+            const int p = row[k];
+            if (p >= 0 && p < P) visible[p] = 1;
+        }
+    }
+}
+
+int visibility_from_idx(dss_ctx *ctx, const int32_t *idx, int64_t num_pixels, int K, int64_t P,
+                        uint8_t *visible, cudaStream_t st) {
+    DSS_CUDA_TRY(cudaMemsetAsync(visible, 0, (size_t)(P > 0 ? P : 0), st));
+    if (num_pixels == 0 || P == 0) return DSS_OK;
+    visibility_kernel<<<nblocks(num_pixels, 256, ctx->sm_count, 16), 256, 0, st>>>(idx, num_pixels, K, P, visible);
+    DSS_LAUNCH_CHECK(ctx);
+    return DSS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Search radius: radii_s * lower median of the flattened (rx, ry) of the view's visible points
+// (rasterizer.py:888, torch.median = element (m-1)/2 of the ascending sort of m = 2 n_vis values).
+// Exact 4-pass (8 bits each, MSB first) radix select on the order-preserving uint image of the floats.
+// hist layout: (N, 4, 256) uint32.  Each block first re-derives the prefix chosen by the previous
+// passes from their (complete) histograms -- 256-bin scans, negligible -- so no host involvement.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int float_key(float f) {
+    const unsigned int b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key_float(unsigned int k) {
+    const unsigned int b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+    return __uint_as_float(b);
+}
+
+// Walk histograms of passes [0, upto) and return (prefix, remaining rank).  Executed by one warp.
+__device__ void select_resolve(const unsigned int *hist_n, int upto, unsigned int &prefix,
+                               unsigned long long &rank, unsigned long long &total) {
+    const int lane = threadIdx.x & 31;
+    prefix = 0;
+    rank = 0;
+    total = 0;
+    for (int pass = 0; pass < upto; ++pass) {
+        const unsigned int *h = hist_n + pass * 256;
+        // each lane owns 8 consecutive bins
+        unsigned int c[8];
+        unsigned long long s = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            c[j] = h[lane * 8 + j];
+            s += c[j];
+        }
+        unsigned long long incl = s;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        const unsigned long long tot = __shfl_sync(0xffffffffu, incl, 31);
+        if (pass == 0) {
+            total = tot;
+            rank = (tot > 0) ? (tot - 1) / 2 : 0;  // lower median
+        }
+        unsigned long long excl = incl - s;
+        // find the bin containing `rank`
+        int found = -1;
+        unsigned long long found_excl = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (found < 0 && rank >= excl && rank < excl + c[j]) {
+                found = lane * 8 + j;
+                found_excl = excl;
+            }
+            excl += c[j];
+        }
+        const unsigned int who = __ballot_sync(0xffffffffu, found >= 0);
+        int digit = 0;
+        unsigned long long dexcl = 0;
+        if (who) {
+            const int src = __ffs(who) - 1;
+            digit = __shfl_sync(0xffffffffu, found, src);
+            dexcl = __shfl_sync(0xffffffffu, found_excl, src);
+        }
+        prefix = (prefix << 8) | (unsigned int)digit;
+        rank -= dexcl;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+select_hist_kernel(const float4 *__restrict__ rec, const float *__restrict__ radii,
+                   const uint8_t *__restrict__ visible, const int64_t *__restrict__ first_idx,
+                   const int64_t *__restrict__ num_points, int64_t P0_shared, int pass,
+                   unsigned int *__restrict__ hist) {
+    __shared__ unsigned int s_hist[256];
+    __shared__ unsigned int s_prefix;
+    const int n = blockIdx.y;
+    unsigned int *hist_n = hist + (int64_t)n * 4 * 256;
+    s_hist[threadIdx.x] = 0;
+    if (threadIdx.x < 32) {
+        unsigned int prefix;
+        unsigned long long rank, total;
+        select_resolve(hist_n, pass, prefix, rank, total);
+        if (threadIdx.x == 0) s_prefix = prefix;
+    }
+    __syncthreads();
+    const unsigned int prefix = s_prefix;
+    const int shift = 24 - 8 * pass;
+    const ViewRange vr = view_range(first_idx, num_points, n, P0_shared);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < vr.count;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = vr.first + i;
+        if (!visible[p]) continue;
+        float rx, ry;
+        if (rec) {
+            rx = __ldg(&rec[2 * p]).w;
+            ry = __ldg(&rec[2 * p + 1]).x;
+        } else {
+            rx = radii[p * 2];
+            ry = radii[p * 2 + 1];
+        }
+        const unsigned int kx = float_key(rx), ky = float_key(ry);
+        if (pass == 0 || (kx >> (shift + 8)) == prefix) atomicAdd(&s_hist[(kx >> shift) & 255u], 1u);
+        if (pass == 0 || (ky >> (shift + 8)) == prefix) atomicAdd(&s_hist[(ky >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    const unsigned int v = s_hist[threadIdx.x];
+    if (v) atomicAdd(&hist_n[pass * 256 + threadIdx.x], v);
+}
+
+__global__ void select_final_kernel(const unsigned int *__restrict__ hist, float radii_s, float *__restrict__ rs) {
+    const int n = blockIdx.x;
+    unsigned int prefix;
+    unsigned long long rank, total;
+    select_resolve(hist + (int64_t)n * 4 * 256, 4, prefix, rank, total);
+    if (threadIdx.x == 0) rs[n] = (total > 0) ? key_float(prefix) * radii_s : 0.0f;
+}
+
+int search_radius(dss_ctx *ctx, const float4 *rec, const float *radii, const uint8_t *visible,
+                  const int64_t *first_idx, const int64_t *num_points, int N, int64_t P0, float radii_s,
+                  float *rs, cudaStream_t st) {
+    if (N <= 0) return DSS_OK;
+    unsigned int *hist = nullptr;
+    int rc = ctx_get(ctx, BUF_SELECT, (size_t)N * 4 * 256, &hist);
+    if (rc) return rc;
+    DSS_CUDA_TRY(cudaMemsetAsync(hist, 0, (size_t)N * 4 * 256 * sizeof(unsigned int), st));
+    if (P0 > 0) {
+        dim3 grid(nblocks(P0, 256, ctx->sm_count, 4), N);
+        for (int pass = 0; pass < 4; ++pass) {
+            select_hist_kernel<<<grid, 256, 0, st>>>(rec, radii, visible, first_idx, num_points, P0, pass, hist);
+            DSS_LAUNCH_CHECK(ctx);
+        }
+    }
+    select_final_kernel<<<N, 32, 0, st>>>(hist, radii_s, rs);
+    DSS_LAUNCH_CHECK(ctx);
+    return DSS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Occupancy gather.  One warp per visible splat; lanes stride over the (2R+1)^2 pixel window that
+// conservatively contains the disc of radius r_n, evaluate the reference's per-pair rule
+// (rasterize_points_backward.cu:141-178) and warp-reduce.  32 consecutive splats per warp, the visible
+// ones are processed in turn; each lane finally stores the result of "its" splat (coalesced float2).
+// ---------------------------------------------------------------------------------------------
+constexpr int OCC_WARPS = 8;
+
+__global__ void __launch_bounds__(OCC_WARPS * 32)
+occ_backward_kernel(const float4 *__restrict__ rec, const uint8_t *__restrict__ visible,
+                    const float *__restrict__ rs, const float *__restrict__ grad, int pix_stride,
+                    int pix_offset, const int64_t *__restrict__ first_idx,
+                    const int64_t *__restrict__ num_points, int64_t P0_shared, int S,
+                    float2 *__restrict__ grad_xy) {
+    const int n = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const ViewRange vr = view_range(first_idx, num_points, n, P0_shared);
+    const float r = rs[n];
+    const float r2 = r * r;
+    const bool pow2 = (S & (S - 1)) == 0;
+    const float inv_S = 1.0f / (float)S;
+    const float half_S = 0.5f * (float)S;
+    const float *gview = grad + ((int64_t)n * S * S) * pix_stride + pix_offset;
+    constexpr unsigned FULL = 0xffffffffu;
+
+    for (int64_t g0 = ((int64_t)blockIdx.x * OCC_WARPS + warp) * 32; g0 < vr.count;
+         g0 += (int64_t)gridDim.x * OCC_WARPS * 32) {
+        const int64_t i = g0 + lane;
+        const bool in_range = i < vr.count;
+        const int64_t p = vr.first + i;
+        float4 A = make_float4(0.f, 0.f, -1.f, 0.f);
+        float ry = 0.f;
+        bool vis = false;
+        if (in_range) {
+            vis = visible[p] != 0;
+            if (vis) {
+                A = __ldg(&rec[2 * p]);
+                ry = __ldg(&rec[2 * p + 1]).x;
+                // rasterize_points_backward.cu:145 -- outside the renderable area
+                if (A.z < 0.0f || fabsf(A.y) > 1.0f || fabsf(A.x) > 1.0f) vis = false;
+            }
+        }
+        float out_x = 0.f, out_y = 0.f;
+        unsigned todo = __ballot_sync(FULL, vis);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const float px = __shfl_sync(FULL, A.x, src);
+            const float py = __shfl_sync(FULL, A.y, src);
+            const float rx = __shfl_sync(FULL, A.w, src);
+            const float ryb = __shfl_sync(FULL, ry, src);
+            // conservative window in NDC-index space: pixel i has centre -1 + (2i+1)/S
+            // (clamped in float first: saturating conversions of huge radii must not wrap)
+            const float top = (float)(S - 1);
+            const int xi_lo = (int)fminf(fmaxf(floorf((px - r + 1.0f) * half_S - 0.5f) - 1.0f, 0.0f), top + 1.0f);
+            const int xi_hi = (int)fmaxf(fminf(ceilf((px + r + 1.0f) * half_S - 0.5f) + 1.0f, top), -1.0f);
+            const int yi_lo = (int)fminf(fmaxf(floorf((py - r + 1.0f) * half_S - 0.5f) - 1.0f, 0.0f), top + 1.0f);
+            const int yi_hi = (int)fmaxf(fminf(ceilf((py + r + 1.0f) * half_S - 0.5f) + 1.0f, top), -1.0f);
+            const int W = xi_hi - xi_lo + 1, H = yi_hi - yi_lo + 1;
+            float gx = 0.f, gy = 0.f;
+            if (W > 0 && H > 0) {
+                const int total = W * H;
+                int wy = lane / W, wx = lane - wy * W;
+                const int step_y = 32 / W, step_x = 32 - step_y * W;
+                for (int w = lane; w < total; w += 32) {
+                    const int xi = xi_lo + wx, yi = yi_lo + wy;
+                    const float g = __ldg(gview + ((int64_t)(S - 1 - yi) * S + (S - 1 - xi)) * pix_stride);
+                    if (g != 0.0f) {
+                        const float xf = pix_to_ndc_fast(xi, S, inv_S, pow2);
+                        const float yf = pix_to_ndc_fast(yi, S, inv_S, pow2);
+                        const float dx = xf - px, dy = yf - py;
+                        const float d2 = dx * dx + dy * dy;
+                        const bool outside = (fabsf(dx) > rx) || (fabsf(dy) > ryb);
+                        if (!(d2 > r2) && !(g > 0.0f && outside)) {
+                            const float den = eps_denom(d2, 1e-10f);
+                            gx += dx / den * g;
+                            gy += dy / den * g;
+                        }
+                    }
+                    wx += step_x;
+                    wy += step_y;
+                    if (wx >= W) {
+                        wx -= W;
+                        wy += 1;
+                    }
+                }
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                gx += __shfl_xor_sync(FULL, gx, d);
+                gy += __shfl_xor_sync(FULL, gy, d);
+            }
+            if (lane == src) {
+                out_x = gx;
+                out_y = gy;
+            }
+        }
+        if (in_range) grad_xy[p] = make_float2(out_x, out_y);
+    }
+}
+
+int occ_backward(dss_ctx *ctx, const float4 *rec, const uint8_t *visible, const float *rs,
+                 const float *grad_occ, int pix_stride, int pix_offset, const int64_t *first_idx,
+                 const int64_t *num_points, int N, int64_t P0, int S, float *grad_xy, cudaStream_t st) {
+    if (N <= 0 || P0 <= 0) return DSS_OK;
+    dim3 grid(nblocks(P0, OCC_WARPS * 32, ctx->sm_count, 64), N);
+    occ_backward_kernel<<<grid, OCC_WARPS * 32, 0, st>>>(rec, visible, rs, grad_occ, pix_stride, pix_offset,
+                                                         first_idx, num_points, P0, S,
+                                                         reinterpret_cast<float2 *>(grad_xy));
+    DSS_LAUNCH_CHECK(ctx);
+    return DSS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// z-buffer backward (rasterize_points.cu:823-846).  z_grad element stride in floats (1 for (P,),
+// 3 to write the z column of a (P,3) gradient).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+zbuf_backward_kernel(const int32_t *__restrict__ idx, const float *__restrict__ grad_zbuf, int64_t num_pixels,
+                     int K, float *z_grad, int z_stride) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < num_pixels;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        for (int k = 0; k < K; ++k) {
+            const float g = grad_zbuf[i * K + k];
+            if (g == 0.0f) continue;
+            const int p = idx[i * K + k];
+            if (p < 0) break;
+            atomicAdd(z_grad + (int64_t)p * z_stride, g);
+        }
+    }
+}
+
+int zbuf_backward(dss_ctx *ctx, const int32_t *idx, const float *grad_zbuf, int64_t num_pixels, int K,
+                  float *z_grad, int z_stride, cudaStream_t st) {
+    if (num_pixels == 0) return DSS_OK;
+    zbuf_backward_kernel<<<nblocks(num_pixels, 256, ctx->sm_count, 16), 256, 0, st>>>(idx, grad_zbuf, num_pixels,
+                                                                                      K, z_grad, z_stride);
+    DSS_LAUNCH_CHECK(ctx);
+    return DSS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Colour backward: dL/dcolour[idx_k] += g_rgb * w_k / max(sum w, 1e-4)  (norm_weighted_sum backward [ext]);
+// `weights` already holds the normalised weights written by the forward pass.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+colour_backward_kernel(const int32_t *__restrict__ idx, const float *__restrict__ weights,
+                       const float4 *__restrict__ grad_image, int64_t num_pixels, int K,
+                       float *grad_colours) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < num_pixels;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        if (idx[i * K] < 0) continue;
+        const float4 g = __ldg(&grad_image[i]);
+        if (g.x == 0.0f && g.y == 0.0f && g.z == 0.0f) continue;
+        for (int k = 0; k < K; ++k) {
+            const int p = idx[i * K + k];
+            if (p < 0) break;
+            const float w = weights[i * K + k];
+            float *dst = grad_colours + (int64_t)p * 3;
+            atomicAdd(dst + 0, g.x * w);
+            atomicAdd(dst + 1, g.y * w);
+            atomicAdd(dst + 2, g.z * w);
+        }
+    }
+}
+
+int colour_backward(dss_ctx *ctx, const int32_t *idx, const float *weights, const float *grad_image,
+                    int64_t num_pixels, int K, float *grad_colours, cudaStream_t st) {
+    if (num_pixels == 0) return DSS_OK;
+    colour_backward_kernel<<<nblocks(num_pixels, 256, ctx->sm_count, 16), 256, 0, st>>>(
+        idx, weights, reinterpret_cast<const float4 *>(grad_image), num_pixels, K, grad_colours);
+    DSS_LAUNCH_CHECK(ctx);
+    return DSS_OK;
+}
+
+}  // namespace dss
+
+extern "C" {
+
+int dss_visibility_from_idx(dss_ctx *ctx, const int32_t *idx, int64_t num_pixels, int K, int64_t P,
+                            uint8_t *visible, void *stream) {
+    DSS_REQUIRE(ctx != nullptr, "ctx is null");
+    DSS_REQUIRE(num_pixels >= 0 && K > 0 && P >= 0, "bad size");
+    DSS_REQUIRE((num_pixels == 0 || idx) && (P == 0 || visible), "null pointer");
+    return dss::visibility_from_idx(ctx, idx, num_pixels, K, P, visible, (cudaStream_t)stream);
+}
+
+int dss_search_radius(dss_ctx *ctx, const float *radii, const uint8_t *visible, const int64_t *first_idx,
+                      const int64_t *num_points, int N, int64_t P, float radii_s, float *rs, void *stream) {
+    DSS_REQUIRE(ctx != nullptr, "ctx is null");
+    DSS_REQUIRE(N >= 0 && P >= 0, "negative size");
+    if (N == 0) return DSS_OK;
+    DSS_REQUIRE(rs && first_idx && num_points && (P == 0 || (radii && visible)), "null pointer");
+    return dss::search_radius(ctx, nullptr, radii, visible, first_idx, num_points, N, P, radii_s, rs,
+                              (cudaStream_t)stream);
+}
+
+int dss_occ_backward(dss_ctx *ctx, const float *points, const float *radii, const uint8_t *visible,
+                     const float *rs, const float *grad_occ, int pix_stride, int pix_offset,
+                     const int64_t *first_idx, const int64_t *num_points, int N, int64_t P, int image_size,
+                     float *grad_xy, void *stream) {
+    using namespace dss;
+    cudaStream_t st = (cudaStream_t)stream;
+    DSS_REQUIRE(ctx != nullptr, "ctx is null");
+    DSS_REQUIRE(N >= 0 && P >= 0 && image_size > 0, "bad size");
+    DSS_REQUIRE(pix_stride >= 1 && pix_offset >= 0 && pix_offset < pix_stride, "bad pixel stride/offset");
+    if (N == 0 || P == 0) return DSS_OK;
+    DSS_REQUIRE(points && radii && visible && rs && grad_occ && first_idx && num_points && grad_xy, "null pointer");
+    float4 *rec = nullptr;
+    int rc;
+    if ((rc = ctx_get(ctx, BUF_RECORDS, (size_t)(2 * P), &rec))) return rc;
+    if ((rc = pack_records(ctx, points, radii, nullptr, P, rec, st))) return rc;
+    DSS_CUDA_TRY(cudaMemsetAsync(grad_xy, 0, (size_t)P * 2 * sizeof(float), st));
+    return occ_backward(ctx, rec, visible, rs, grad_occ, pix_stride, pix_offset, first_idx, num_points, N, P,
+                        image_size, grad_xy, st);
+}
+
+int dss_zbuf_backward(dss_ctx *ctx, const int32_t *idx, const float *grad_zbuf, int64_t num_pixels, int K,
+                      float *z_grad, void *stream) {
+    DSS_REQUIRE(ctx != nullptr, "ctx is null");
+    DSS_REQUIRE(num_pixels >= 0 && K > 0, "bad size");
+    if (num_pixels == 0) return DSS_OK;
+    DSS_REQUIRE(idx && grad_zbuf && z_grad, "null pointer");
+    return dss::zbuf_backward(ctx, idx, grad_zbuf, num_pixels, K, z_grad, 1, (cudaStream_t)stream);
+}
+
+}  // extern "C"

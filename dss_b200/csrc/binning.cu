@@ -1,0 +1,275 @@
+// binning.cu -- splat records, screen-tile binning (count -> scan -> scatter), 2-D grid binning.
+//
+// Replaces RasterizePointsCoarseCuda (DSS/csrc/rasterize_points.cu:293-500): instead of a dense
+// (N,B,B,M) int32 tensor filled by 64 CTAs that brute-force all B^2 bins per point, every splat
+// computes its bin rectangle in O(1), counts go through an on-device exclusive scan and ids are
+// scattered into exact-size CSR lists.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace dss {
+
+// ---------------------------------------------------------------------------------------------
+// pack: (points (P,3), radii (P,2), ellipse (P,3)) -> 32-byte records
+//   rec[2p]   = {px, py, pz, rx}
+//   rec[2p+1] = {ry, a, b, c}
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pack_records_kernel(const float *__restrict__ points, const float *__restrict__ radii,
+                    const float *__restrict__ ellipse, int64_t P, float4 *__restrict__ rec) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    float a = 0.f, b = 0.f, c = 0.f;
+    if (ellipse) {
+        a = ellipse[p * 3 + 0];
+        b = ellipse[p * 3 + 1];
+        c = ellipse[p * 3 + 2];
+    }
+    rec[2 * p] = make_float4(points[p * 3 + 0], points[p * 3 + 1], points[p * 3 + 2], radii[p * 2 + 0]);
+    rec[2 * p + 1] = make_float4(radii[p * 2 + 1], a, b, c);
+}
+
+int pack_records(dss_ctx *ctx, const float *points, const float *radii, const float *ellipse, int64_t P,
+                 float4 *rec, cudaStream_t st) {
+    if (P == 0) return DSS_OK;
+    pack_records_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(points, radii, ellipse, P, rec);
+    DSS_LAUNCH_CHECK(ctx);
+    return DSS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Bin range of an interval [p0, p1] -- the reference's closed fp32 predicate
+//     (p0 <= b1(b)) && (b0(b) <= p1),   b0(b) = PixToNdc(b*bin) - 1/S,  b1(b) = PixToNdc((b+1)*bin-1) + 1/S
+// (DSS/csrc/rasterize_points.cu:355-383) is monotone in b, so the overlapping bins form a contiguous
+// range [lo, hi].  We estimate it arithmetically and fix it up with the exact predicate, which makes
+// the membership bit-identical to the reference's brute-force loop at O(1) cost.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float bin_lo_edge(int b, int bin, int S, float half_pix) {
+    return pix_to_ndc(b * bin, S) - half_pix;
+}
+__device__ __forceinline__ float bin_hi_edge(int b, int bin, int S, float half_pix) {
+    return pix_to_ndc((b + 1) * bin - 1, S) + half_pix;
+}
+
+__device__ __forceinline__ void bin_range(float p0, float p1, int bin, int S, int B, int &lo, int &hi) {
+    const float half_pix = 1.0f / S;
+    const float scale = (float)S / (2.0f * (float)bin);
+    // estimates (may be off by one or two; NaN/inf handled by the clamps and the exact fix-up)
+    float e0 = floorf((p0 + 1.0f) * scale) - 1.0f;
+    float e1 = floorf((p1 + 1.0f) * scale) + 1.0f;
+    lo = (e0 >= 0.0f) ? ((e0 < (float)B) ? (int)e0 : B) : 0;          // NaN -> 0
+    hi = (e1 >= 0.0f) ? ((e1 < (float)B) ? (int)e1 : B - 1) : -1;    // NaN -> -1
+    if (hi > B - 1) hi = B - 1;
+    // lo = smallest b with p0 <= b1(b)
+    while (lo > 0 && p0 <= bin_hi_edge(lo - 1, bin, S, half_pix)) --lo;
+    while (lo < B && !(p0 <= bin_hi_edge(lo, bin, S, half_pix))) ++lo;
+    // hi = largest b with b0(b) <= p1
+    while (hi < B - 1 && bin_lo_edge(hi + 1, bin, S, half_pix) <= p1) ++hi;
+    while (hi >= 0 && !(bin_lo_edge(hi, bin, S, half_pix) <= p1)) --hi;
+}
+
+struct BinRect {
+    int x0, x1, y0, y1;
+    bool empty;
+};
+
+__device__ __forceinline__ BinRect splat_bin_rect(const float4 A, const float ry, int bin, int S, int B) {
+    BinRect r;
+    r.empty = true;
+    r.x0 = r.y0 = 0;
+    r.x1 = r.y1 = -1;
+    if (A.z < 0) return r;  // behind the camera (rasterize_points.cu:351-352); also NaN-safe below
+    const float px0 = A.x - A.w, px1 = A.x + A.w;
+    const float py0 = A.y - ry, py1 = A.y + ry;
+    bin_range(py0, py1, bin, S, B, r.y0, r.y1);
+    if (r.y0 > r.y1) return r;
+    bin_range(px0, px1, bin, S, B, r.x0, r.x1);
+    if (r.x0 > r.x1) return r;
+    r.empty = false;
+    return r;
+}
+
+// grid: (blocks, N).  counts: (N*B*B) zero-initialised.
+__global__ void __launch_bounds__(256)
+bin_count_kernel(const float4 *__restrict__ rec, const int64_t *__restrict__ first_idx,
+                 const int64_t *__restrict__ num_points, int64_t P0_shared, int S, int bin, int B,
+                 int32_t *__restrict__ counts) {
+    const int n = blockIdx.y;
+    const ViewRange vr = view_range(first_idx, num_points, n, P0_shared);
+    int32_t *cnt = counts + (int64_t)n * B * B;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < vr.count;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = vr.first + i;
+        const float4 A = __ldg(&rec[2 * p]);
+        const float ry = __ldg(&rec[2 * p + 1]).x;
+        const BinRect r = splat_bin_rect(A, ry, bin, S, B);
+        if (r.empty) continue;
+        for (int by = r.y0; by <= r.y1; ++by)
+            for (int bx = r.x0; bx <= r.x1; ++bx) atomicAdd(&cnt[by * B + bx], 1);
+    }
+}
+
+// cursors: copy of offsets (N*B*B), advanced atomically; ids: CSR payload.
+__global__ void __launch_bounds__(256)
+bin_scatter_kernel(const float4 *__restrict__ rec, const int64_t *__restrict__ first_idx,
+                   const int64_t *__restrict__ num_points, int64_t P0_shared, int S, int bin, int B,
+                   int32_t *__restrict__ cursors, int32_t *__restrict__ ids) {
+    const int n = blockIdx.y;
+    const ViewRange vr = view_range(first_idx, num_points, n, P0_shared);
+    int32_t *cur = cursors + (int64_t)n * B * B;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < vr.count;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = vr.first + i;
+        const float4 A = __ldg(&rec[2 * p]);
+        const float ry = __ldg(&rec[2 * p + 1]).x;
+        const BinRect r = splat_bin_rect(A, ry, bin, S, B);
+        if (r.empty) continue;
+        for (int by = r.y0; by <= r.y1; ++by)
+            for (int bx = r.x0; bx <= r.x1; ++bx) {
+                const int slot = atomicAdd(&cur[by * B + bx], 1);
+                ids[slot] = (int32_t)p;
+            }
+    }
+}
+
+static inline unsigned int blocks_for(int64_t work_items, int threads, int sm_count, int per_sm) {
+    int64_t b = (work_items + threads - 1) / threads;
+    const int64_t cap = (int64_t)sm_count * per_sm;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (unsigned int)b;
+}
+
+// count + scan.  offsets must have N*B*B + 1 entries; counts N*B*B + 1 (last stays 0).
+int bin_count_and_scan(dss_ctx *ctx, const float4 *rec, const int64_t *first_idx, const int64_t *num_points,
+                       int N, int64_t P0, int S, int bin, int32_t *counts, int32_t *offsets, cudaStream_t st) {
+    const int B = 1 + (S - 1) / bin;
+    const int64_t nb = (int64_t)N * B * B;
+    DSS_CUDA_TRY(cudaMemsetAsync(counts, 0, (size_t)(nb + 1) * sizeof(int32_t), st));
+    if (P0 > 0) {
+        dim3 grid(blocks_for(P0, 256, ctx->sm_count, 8), N);
+        bin_count_kernel<<<grid, 256, 0, st>>>(rec, first_idx, num_points, P0, S, bin, B, counts);
+        DSS_LAUNCH_CHECK(ctx);
+    }
+    return exclusive_scan_i32(ctx, counts, offsets, nb + 1, st);
+}
+
+int bin_scatter(dss_ctx *ctx, const float4 *rec, const int64_t *first_idx, const int64_t *num_points, int N,
+                int64_t P0, int S, int bin, const int32_t *offsets, int32_t *cursors, int32_t *ids,
+                cudaStream_t st) {
+    const int B = 1 + (S - 1) / bin;
+    const int64_t nb = (int64_t)N * B * B;
+    DSS_CUDA_TRY(cudaMemcpyAsync(cursors, offsets, (size_t)nb * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    if (P0 > 0) {
+        dim3 grid(blocks_for(P0, 256, ctx->sm_count, 8), N);
+        bin_scatter_kernel<<<grid, 256, 0, st>>>(rec, first_idx, num_points, P0, S, bin, B, cursors, ids);
+        DSS_LAUNCH_CHECK(ctx);
+    }
+    return DSS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 2-D uniform grid insert / counting sort (FRNN replacements; grid.cu:62-99, counting_sort.cu:5-36).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+grid_insert_2d_kernel(const float *__restrict__ points, const int64_t *__restrict__ lengths,
+                      const float *__restrict__ params, int32_t *grid_cnt, int32_t *__restrict__ grid_cell,
+                      int32_t *__restrict__ grid_idx, int Pmax, int G) {
+    const int n = blockIdx.y;
+    const int64_t len = lengths[n];
+    const float min_x = params[n * 6 + 0], min_y = params[n * 6 + 1], delta = params[n * 6 + 2];
+    const int res_x = (int)params[n * 6 + 3], res_y = (int)params[n * 6 + 4];
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < len;
+         p += (int64_t)gridDim.x * blockDim.x) {
+        const float2 xy = reinterpret_cast<const float2 *>(points)[(int64_t)n * Pmax + p];
+        int gx = (int)((xy.x - min_x) * delta);
+        int gy = (int)((xy.y - min_y) * delta);
+        gx = max(min(gx, res_x - 1), 0);
+        gy = max(min(gy, res_y - 1), 0);
+        const int gs = gx * res_y + gy;
+        grid_cell[(int64_t)n * Pmax + p] = gs;
+        grid_idx[(int64_t)n * Pmax + p] = atomicAdd(&grid_cnt[(int64_t)n * G + gs], 1);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+grid_counting_sort_2d_kernel(const float *__restrict__ points, const int64_t *__restrict__ lengths,
+                             const int32_t *__restrict__ grid_cell, const int32_t *__restrict__ grid_idx,
+                             const int32_t *__restrict__ grid_off, float *__restrict__ sorted_points,
+                             int32_t *__restrict__ sorted_idx, int Pmax, int G) {
+    const int n = blockIdx.y;
+    const int64_t len = lengths[n];
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < len;
+         p += (int64_t)gridDim.x * blockDim.x) {
+        const int cell = grid_cell[(int64_t)n * Pmax + p];
+        const int64_t s = (int64_t)grid_off[(int64_t)n * G + cell] + grid_idx[(int64_t)n * Pmax + p];
+        if (s < 0 || s >= len) continue;  // corrupt offsets: never write out of the view's rows
+        reinterpret_cast<float2 *>(sorted_points)[(int64_t)n * Pmax + s] =
+            reinterpret_cast<const float2 *>(points)[(int64_t)n * Pmax + p];
+        sorted_idx[(int64_t)n * Pmax + s] = (int32_t)p;
+    }
+}
+
+}  // namespace dss
+
+extern "C" {
+
+int dss_grid_insert_points_2d(dss_ctx *ctx, const float *points, const int64_t *lengths, const float *params,
+                              int32_t *grid_cnt, int32_t *grid_cell, int32_t *grid_idx, int N, int Pmax,
+                              int G, void *stream) {
+    DSS_REQUIRE(ctx && points && lengths && params && grid_cnt && grid_cell && grid_idx, "null pointer");
+    DSS_REQUIRE(N >= 0 && Pmax >= 0 && G >= 0, "negative size");
+    if (N == 0 || Pmax == 0) return DSS_OK;
+    dim3 grid(dss::blocks_for(Pmax, 256, ctx->sm_count, 8), N);
+    dss::grid_insert_2d_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(points, lengths, params, grid_cnt,
+                                                                       grid_cell, grid_idx, Pmax, G);
+    DSS_LAUNCH_CHECK(ctx);
+    return DSS_OK;
+}
+
+int dss_grid_counting_sort_2d(dss_ctx *ctx, const float *points, const int64_t *lengths,
+                              const int32_t *grid_cell, const int32_t *grid_idx, const int32_t *grid_off,
+                              float *sorted_points, int32_t *sorted_idx, int N, int Pmax, int G, void *stream) {
+    DSS_REQUIRE(ctx && points && lengths && grid_cell && grid_idx && grid_off && sorted_points && sorted_idx,
+                "null pointer");
+    DSS_REQUIRE(N >= 0 && Pmax >= 0 && G >= 0, "negative size");
+    if (N == 0 || Pmax == 0) return DSS_OK;
+    dim3 grid(dss::blocks_for(Pmax, 256, ctx->sm_count, 8), N);
+    dss::grid_counting_sort_2d_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+        points, lengths, grid_cell, grid_idx, grid_off, sorted_points, sorted_idx, Pmax, G);
+    DSS_LAUNCH_CHECK(ctx);
+    return DSS_OK;
+}
+
+int dss_rasterize_coarse(dss_ctx *ctx, const float *points, const float *radii, const int64_t *first_idx,
+                         const int64_t *num_points, int N, int64_t P, int image_size, int bin_size,
+                         int32_t *bin_offsets, int32_t *bin_ids, int64_t bin_ids_capacity,
+                         int64_t *total_required_host, void *stream) {
+    using namespace dss;
+    cudaStream_t st = (cudaStream_t)stream;
+    DSS_REQUIRE(ctx && points && radii && first_idx && num_points && bin_offsets, "null pointer");
+    DSS_REQUIRE(N > 0 && P >= 0 && image_size > 0 && bin_size > 0, "bad size");
+    const int S = image_size, B = 1 + (S - 1) / bin_size;
+    const int64_t nb = (int64_t)N * B * B;
+    DSS_REQUIRE(nb + 1 < (int64_t)INT32_MAX, "too many bins");
+    float4 *rec = nullptr;
+    int32_t *counts = nullptr;
+    int rc;
+    if ((rc = ctx_get(ctx, BUF_RECORDS, (size_t)(2 * (P > 0 ? P : 1)), &rec))) return rc;
+    if ((rc = ctx_get(ctx, BUF_TILE_COUNTS, (size_t)(nb + 1), &counts))) return rc;
+    if ((rc = pack_records(ctx, points, radii, nullptr, P, rec, st))) return rc;
+    if ((rc = bin_count_and_scan(ctx, rec, first_idx, num_points, N, P, S, bin_size, counts, bin_offsets, st)))
+        return rc;
+    DSS_CUDA_TRY(cudaMemcpyAsync(ctx->h_pinned, bin_offsets + nb, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    DSS_CUDA_TRY(cudaStreamSynchronize(st));
+    const int64_t total = (int64_t)(*reinterpret_cast<int32_t *>(ctx->h_pinned));
+    if (total_required_host) *total_required_host = total;
+    if (total > bin_ids_capacity || (total > 0 && bin_ids == nullptr)) {
+        set_error("bin_ids capacity %lld < required %lld", (long long)bin_ids_capacity, (long long)total);
+        return DSS_E_CAPACITY;
+    }
+    if (total == 0) return DSS_OK;
+    return bin_scatter(ctx, rec, first_idx, num_points, N, P, S, bin_size, bin_offsets, counts, bin_ids, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,119 @@
+// common.cuh -- context, error handling and small device helpers shared by every kernel file.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/dss_b200.h"
+
+namespace dss {
+
+void set_error(const char *fmt, ...);
+
+#define DSS_CUDA_TRY(expr)                                                                      \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) {                                                                \
+            dss::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,    \
+                           __LINE__);                                                           \
+            return DSS_E_CUDA;                                                                  \
+        }                                                                                       \
+    } while (0)
+
+#define DSS_REQUIRE(cond, msg)                                                                  \
+    do {                                                                                        \
+        if (!(cond)) {                                                                          \
+            dss::set_error("invalid argument: %s (%s)", msg, #cond);                            \
+            return DSS_E_INVALID;                                                               \
+        }                                                                                       \
+    } while (0)
+
+#define DSS_LAUNCH_CHECK(ctx)                                                                   \
+    do {                                                                                        \
+        (ctx)->launches++;                                                                      \
+        cudaError_t _e = cudaGetLastError();                                                    \
+        if (_e != cudaSuccess) {                                                                \
+            dss::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e),          \
+                           __FILE__, __LINE__);                                                 \
+            return DSS_E_CUDA;                                                                  \
+        }                                                                                       \
+    } while (0)
+
+// grow-only scratch slots
+enum BufId {
+    BUF_SCAN_STATUS = 0,
+    BUF_RECORDS,      // packed 32-byte splat records (2 x float4 per splat)
+    BUF_TILE_COUNTS,  // per (view, tile) counts, then cursors
+    BUF_TILE_OFFSETS, // exclusive offsets (+1)
+    BUF_TILE_IDS,     // CSR id lists
+    BUF_SELECT,       // radix-select histograms
+    BUF_MISC,
+    BUF_VIS,
+    BUF_RS,
+    BUF_GRADXY,
+    BUF_CUTOFF,
+    NUM_BUFS
+};
+
+}  // namespace dss
+
+struct dss_ctx {
+    int device;
+    int sm_count;
+    void *buf[dss::NUM_BUFS];
+    size_t cap[dss::NUM_BUFS];
+    int64_t launches;
+    int64_t *h_pinned;  // small pinned host area for read-backs
+};
+
+namespace dss {
+
+int ctx_reserve(dss_ctx *ctx, BufId id, size_t bytes, void **out);
+
+template <typename T>
+inline int ctx_get(dss_ctx *ctx, BufId id, size_t count, T **out) {
+    void *p = nullptr;
+    int rc = ctx_reserve(ctx, id, count * sizeof(T), &p);
+    *out = reinterpret_cast<T *>(p);
+    return rc;
+}
+
+// ---- device helpers -------------------------------------------------------------------------
+
+// Pixel index -> NDC centre, the reference's expression (DSS/csrc/rasterization_utils.cuh:8-11).
+// No multiply-add pair, so immune to FMA contraction: int->float, add, IEEE divide, add.
+__device__ __forceinline__ float pix_to_ndc(int i, int S) { return -1 + (2 * i + 1.0f) / S; }
+
+// Same value without the division when S is a power of two: (2i+1)/S is then exact, so the single
+// rounding of the fused multiply-add equals the single rounding of the reference's final add.
+__device__ __forceinline__ float pix_to_ndc_fast(int i, int S, float inv_S, bool pow2) {
+    return pow2 ? fmaf((float)(2 * i + 1), inv_S, -1.0f) : pix_to_ndc(i, S);
+}
+
+// Sign-preserving clamp of a denominator (DSS/csrc/rasterization_utils.cuh:37-43) with zero treated as
+// positive like the Python helper (DSS/utils/mathHelper.py:10-14); see DESIGN.md hazard 11.
+__device__ __forceinline__ float eps_denom(float d, float eps) {
+    const float a = fmaxf(fabsf(d), eps);
+    return d < 0.0f ? -a : a;
+}
+
+struct ViewRange {
+    int64_t first;
+    int64_t count;
+};
+
+__device__ __forceinline__ ViewRange view_range(const int64_t *first_idx, const int64_t *num_points, int n,
+                                                int64_t P0_shared) {
+    ViewRange r;
+    if (first_idx == nullptr) {
+        r.first = (int64_t)n * P0_shared;
+        r.count = P0_shared;
+    } else {
+        r.first = first_idx[n];
+        r.count = num_points[n];
+    }
+    return r;
+}
+
+}  // namespace dss

@@ -1,0 +1,241 @@
+// ctx.cu -- context lifetime, error strings, grow-only scratch, single-pass exclusive scan.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace dss {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int ctx_reserve(dss_ctx *ctx, BufId id, size_t bytes, void **out) {
+    if (bytes < 256) bytes = 256;
+    if (ctx->cap[id] < bytes) {
+        // grow geometrically; cudaFree waits for kernels still using the old block
+        size_t want = bytes + bytes / 2;
+        want = (want + 255) & ~size_t(255);
+        if (ctx->buf[id]) {
+            cudaFree(ctx->buf[id]);
+            ctx->buf[id] = nullptr;
+            ctx->cap[id] = 0;
+        }
+        void *p = nullptr;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            e = cudaMalloc(&p, bytes);  // retry without the slack
+            want = bytes;
+        }
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            set_error("scratch allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+            return DSS_E_NOMEM;
+        }
+        ctx->buf[id] = p;
+        ctx->cap[id] = want;
+    }
+    *out = ctx->buf[id];
+    return DSS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Exclusive scan, single pass with decoupled look-back.  Replaces external/prefix_sum
+// (Blelloch + recursion + cudaMalloc/cudaFree per level: prefix_sum.cu:135-205).
+// One tile = 256 threads x 8 items.  status word: [63:32] flag (0 none, 1 aggregate, 2 inclusive),
+// [31:0] value.  Tiles are claimed through an atomic ticket so look-back never waits on a tile
+// that has not started.
+// ---------------------------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_kernel(const int32_t *in, int32_t *out, int64_t n, unsigned long long *status,
+            unsigned int *ticket) {
+    __shared__ int32_t s_data[SCAN_TILE];
+    __shared__ int32_t s_warp[SCAN_THREADS / 32];
+    __shared__ unsigned int s_tile;
+    __shared__ int32_t s_prefix;
+
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const unsigned int tile = s_tile;
+    const int64_t base = (int64_t)tile * SCAN_TILE;
+
+    // coalesced (striped) load into shared memory
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; ++j) {
+        const int o = j * SCAN_THREADS + threadIdx.x;
+        const int64_t g = base + o;
+        s_data[o] = (g < n) ? in[g] : 0;
+    }
+    __syncthreads();
+
+    // each thread scans 8 consecutive items (blocked arrangement)
+    int32_t v[SCAN_ITEMS];
+    int32_t sum = 0;
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; ++j) {
+        v[j] = s_data[threadIdx.x * SCAN_ITEMS + j];
+        sum += v[j];
+    }
+    // block-wide exclusive scan of per-thread sums
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int32_t incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int32_t w = (lane < SCAN_THREADS / 32) ? s_warp[lane] : 0;
+#pragma unroll
+        for (int d = 1; d < SCAN_THREADS / 32; d <<= 1) {
+            const int32_t t = __shfl_up_sync(0xffffffffu, w, d);
+            if (lane >= d) w += t;
+        }
+        if (lane < SCAN_THREADS / 32) s_warp[lane] = w;  // inclusive over warps
+    }
+    __syncthreads();
+    const int32_t warp_excl = (warp == 0) ? 0 : s_warp[warp - 1];
+    const int32_t thread_excl = warp_excl + incl - sum;
+    const int32_t tile_total = s_warp[SCAN_THREADS / 32 - 1];
+
+    // publish aggregate / look back (warp 0)
+    if (warp == 0) {
+        if (tile == 0) {
+            if (lane == 0) {
+                atomicExch(&status[0], (2ull << 32) | (unsigned int)tile_total);
+                s_prefix = 0;
+            }
+        } else {
+            if (lane == 0) atomicExch(&status[tile], (1ull << 32) | (unsigned int)tile_total);
+            int32_t running = 0;
+            int64_t look = (int64_t)tile - 1;
+            while (true) {
+                const int64_t t = look - lane;
+                unsigned long long s = (2ull << 32);  // tiles before 0 act as inclusive zero
+                if (t >= 0) {
+                    do {
+                        s = *((volatile unsigned long long *)&status[t]);
+                    } while ((s >> 32) == 0ull);
+                }
+                const unsigned int flag = (unsigned int)(s >> 32);
+                const int32_t val = (int32_t)(unsigned int)(s & 0xffffffffull);
+                // first lane (closest tile is lane 0) that holds an inclusive prefix terminates the walk
+                const unsigned int incl_mask = __ballot_sync(0xffffffffu, flag == 2u);
+                int32_t contrib = val;
+                if (incl_mask) {
+                    const int first = __ffs(incl_mask) - 1;
+                    if (lane > first) contrib = 0;
+                }
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
+                running += contrib;
+                if (incl_mask) break;
+                look -= 32;
+            }
+            if (lane == 0) {
+                atomicExch(&status[tile], (2ull << 32) | (unsigned int)(running + tile_total));
+                s_prefix = running;
+            }
+        }
+    }
+    __syncthreads();
+    const int32_t prefix = s_prefix;
+
+    int32_t run = prefix + thread_excl;
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; ++j) {
+        s_data[threadIdx.x * SCAN_ITEMS + j] = run;
+        run += v[j];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; ++j) {
+        const int o = j * SCAN_THREADS + threadIdx.x;
+        const int64_t g = base + o;
+        if (g < n) out[g] = s_data[o];
+    }
+}
+
+int exclusive_scan_i32(dss_ctx *ctx, const int32_t *in, int32_t *out, int64_t n, cudaStream_t st) {
+    if (n <= 0) return DSS_OK;
+    const int64_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    unsigned long long *status = nullptr;
+    int rc = ctx_get(ctx, BUF_SCAN_STATUS, (size_t)tiles + 1, &status);
+    if (rc) return rc;
+    DSS_CUDA_TRY(cudaMemsetAsync(status, 0, ((size_t)tiles + 1) * sizeof(unsigned long long), st));
+    unsigned int *ticket = reinterpret_cast<unsigned int *>(status + tiles);
+    scan_kernel<<<(unsigned int)tiles, SCAN_THREADS, 0, st>>>(in, out, n, status, ticket);
+    DSS_LAUNCH_CHECK(ctx);
+    return DSS_OK;
+}
+
+}  // namespace dss
+
+extern "C" {
+
+int dss_version(void) { return 1; }
+
+const char *dss_last_error(void) { return dss::g_err; }
+
+int dss_create(dss_ctx **out) {
+    DSS_REQUIRE(out != nullptr, "out pointer is null");
+    int dev = 0;
+    DSS_CUDA_TRY(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    DSS_CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major < 10) {
+        dss::set_error("libdss_b200 is built for sm_100a only; device %d is sm_%d%d", dev, prop.major,
+                       prop.minor);
+        return DSS_E_CUDA;
+    }
+    dss_ctx *c = new dss_ctx();
+    memset(c, 0, sizeof(*c));
+    c->device = dev;
+    c->sm_count = prop.multiProcessorCount;
+    if (cudaMallocHost((void **)&c->h_pinned, 64 * sizeof(int64_t)) != cudaSuccess) {
+        cudaGetLastError();
+        delete c;
+        dss::set_error("pinned host allocation failed");
+        return DSS_E_NOMEM;
+    }
+    *out = c;
+    return DSS_OK;
+}
+
+void dss_destroy(dss_ctx *ctx) {
+    if (!ctx) return;
+    for (int i = 0; i < dss::NUM_BUFS; ++i)
+        if (ctx->buf[i]) cudaFree(ctx->buf[i]);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    delete ctx;
+}
+
+size_t dss_scratch_bytes(const dss_ctx *ctx) {
+    size_t s = 0;
+    if (ctx)
+        for (int i = 0; i < dss::NUM_BUFS; ++i) s += ctx->cap[i];
+    return s;
+}
+
+int64_t dss_launch_count(const dss_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int dss_exclusive_scan_i32(dss_ctx *ctx, const int32_t *in, int32_t *out, int64_t n, void *stream) {
+    DSS_REQUIRE(ctx != nullptr, "ctx is null");
+    DSS_REQUIRE(n >= 0, "n must be non-negative");
+    if (n == 0) return DSS_OK;
+    DSS_REQUIRE(in != nullptr && out != nullptr, "null array");
+    return dss::exclusive_scan_i32(ctx, in, out, n, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,61 @@
+// kernels.cuh -- host-side entry points shared between the translation units of libdss_b200.
+#pragma once
+#include "common.cuh"
+
+namespace dss {
+
+constexpr int RASTER_TILE = 16;  // pixels per side of a raster tile (one 256-thread CTA)
+
+int exclusive_scan_i32(dss_ctx *ctx, const int32_t *in, int32_t *out, int64_t n, cudaStream_t st);
+
+int pack_records(dss_ctx *ctx, const float *points, const float *radii, const float *ellipse, int64_t P,
+                 float4 *rec, cudaStream_t st);
+
+int bin_count_and_scan(dss_ctx *ctx, const float4 *rec, const int64_t *first_idx, const int64_t *num_points,
+                       int N, int64_t P0, int S, int bin, int32_t *counts, int32_t *offsets, cudaStream_t st);
+
+int bin_scatter(dss_ctx *ctx, const float4 *rec, const int64_t *first_idx, const int64_t *num_points, int N,
+                int64_t P0, int S, int bin, const int32_t *offsets, int32_t *cursors, int32_t *ids,
+                cudaStream_t st);
+
+struct RasterArgs {
+    const float4 *rec;        // 2 per splat
+    const float *cutoff;      // per point (P,) or nullptr -> cutoff_uniform
+    float cutoff_uniform;
+    const int32_t *tile_offsets;  // (N*B*B + 1)
+    const int32_t *tile_ids;
+    int N, S, K, B;
+    float depth_merge;
+    // outputs
+    int32_t *idx;
+    float *zbuf;     // may be null
+    float *qvalue;   // may be null
+    float *occ;      // may be null (N,S,S)
+    // blend (all null when not blending)
+    const float *scaler;   // (P,)
+    const float *colours;  // (P,3)
+    float *image;          // (N,S,S,4)
+    float *weights;        // (N,S,S,K)
+    uint8_t *visible;      // (P,) must be zeroed by the caller
+};
+
+int raster_forward(dss_ctx *ctx, const RasterArgs &a, cudaStream_t st);
+
+// bin + rasterize, shared by dss_splat_points and dss_render_forward.  Synchronises once.
+int bin_and_raster(dss_ctx *ctx, RasterArgs a, const int64_t *first_idx, const int64_t *num_points,
+                   int64_t P0, cudaStream_t st);
+
+int visibility_from_idx(dss_ctx *ctx, const int32_t *idx, int64_t num_pixels, int K, int64_t P,
+                        uint8_t *visible, cudaStream_t st);
+int search_radius(dss_ctx *ctx, const float4 *rec, const float *radii, const uint8_t *visible,
+                  const int64_t *first_idx, const int64_t *num_points, int N, int64_t P0, float radii_s,
+                  float *rs, cudaStream_t st);
+int occ_backward(dss_ctx *ctx, const float4 *rec, const uint8_t *visible, const float *rs,
+                 const float *grad_occ, int pix_stride, int pix_offset, const int64_t *first_idx,
+                 const int64_t *num_points, int N, int64_t P0, int S, float *grad_xy, cudaStream_t st);
+int zbuf_backward(dss_ctx *ctx, const int32_t *idx, const float *grad_zbuf, int64_t num_pixels, int K,
+                  float *z_grad, int z_stride, cudaStream_t st);
+int colour_backward(dss_ctx *ctx, const int32_t *idx, const float *weights, const float *grad_image,
+                    int64_t num_pixels, int K, float *grad_colours, cudaStream_t st);
+
+}  // namespace dss

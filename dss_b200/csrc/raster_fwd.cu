@@ -1,0 +1,283 @@
+// raster_fwd.cu -- per-tile forward rasterization (+ optional fused blend).
+//
+// Replaces RasterizePointsFineCudaKernel (DSS/csrc/rasterize_points.cu:506-597), whose every pixel
+// loops over all M = max(1e4, P) slots of its bin and keeps a 150-entry queue in local memory, and --
+// when blending -- the weights/compositor/concat sequence of DSS/core/renderer.py:53-78.
+//
+// One 256-thread CTA per 16x16 pixel tile.  The tile's splat list (CSR ids) is streamed through shared
+// memory in chunks of 256 records.  Each warp owns an 8x4 pixel patch and runs a two-level test:
+//   level 1 (lane-parallel, 32 splats at a time): bbox-vs-patch overlap and a depth cull against the
+//            warp's current K-th nearest depth -> ballot;
+//   level 2 (per surviving splat, broadcast from shared memory): the reference's exact per-pixel test
+//            (CheckPixelInsidePoint, rasterize_points.cu:87-97) and a sorted insert into K registers.
+// Selection is by (z, id) lexicographic order, so the result does not depend on list order (the
+// reference's own CPU path pops a max-heap of (z, idx, q) tuples: rasterize_points_cpu.cpp:87-121).
+#include <math_constants.h>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace dss {
+
+constexpr int RASTER_THREADS = RASTER_TILE * RASTER_TILE;  // 256
+constexpr int RASTER_CHUNK = RASTER_THREADS;
+
+__device__ __forceinline__ bool frag_less(float za, int ia, float zb, int ib) {
+    return (za < zb) || (za == zb && ia < ib);
+}
+
+template <int KMAX, bool PER_POINT_CUTOFF, bool BLEND>
+__global__ void __launch_bounds__(RASTER_THREADS)
+raster_fwd_kernel(const __grid_constant__ RasterArgs a) {
+    __shared__ float4 sA[RASTER_CHUNK];
+    __shared__ float4 sB[RASTER_CHUNK];
+    __shared__ int sId[RASTER_CHUNK];
+    __shared__ float sCut[PER_POINT_CUTOFF ? RASTER_CHUNK : 1];
+
+    const int S = a.S, B = a.B, K = a.K;
+    const int n = blockIdx.y;
+    const int tile = blockIdx.x;
+    const int ty = tile / B, tx = tile - ty * B;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr unsigned FULL = 0xffffffffu;
+
+    // NDC-index-space pixel of this thread
+    const int ix0 = tx * RASTER_TILE + (warp & 1) * 8;
+    const int iy0 = ty * RASTER_TILE + (warp >> 1) * 4;
+    const int xi = ix0 + (lane & 7);
+    const int yi = iy0 + (lane >> 3);
+    const bool valid = (xi < S) && (yi < S);
+    const float xf = pix_to_ndc(xi, S);
+    const float yf = pix_to_ndc(yi, S);
+    // warp patch extents, widened by half a pixel (same slack as the reference's bins)
+    const float half_pix = 1.0f / S;
+    const bool patch_live = (ix0 < S) && (iy0 < S);
+    const float pat_x0 = pix_to_ndc(ix0, S) - half_pix;
+    const float pat_x1 = pix_to_ndc(min(ix0 + 7, S - 1), S) + half_pix;
+    const float pat_y0 = pix_to_ndc(iy0, S) - half_pix;
+    const float pat_y1 = pix_to_ndc(min(iy0 + 3, S - 1), S) + half_pix;
+
+    float fz[KMAX], fq[KMAX];
+    int fid[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+        fz[k] = CUDART_INF_F;
+        fq[k] = -1.0f;
+        fid[k] = INT32_MAX;
+    }
+    float thresh = CUDART_INF_F;  // warp-wide max of the KMAX-th nearest depth
+
+    const int64_t tbase = (int64_t)n * B * B + tile;
+    const int beg = a.tile_offsets[tbase], end = a.tile_offsets[tbase + 1];
+
+    for (int base = beg; base < end; base += RASTER_CHUNK) {
+        const int cnt = min(RASTER_CHUNK, end - base);
+        if (tid < cnt) {
+            const int id = a.tile_ids[base + tid];
+            sA[tid] = __ldg(&a.rec[2 * (int64_t)id]);
+            sB[tid] = __ldg(&a.rec[2 * (int64_t)id + 1]);
+            sId[tid] = id;
+            if (PER_POINT_CUTOFF) sCut[tid] = __ldg(&a.cutoff[id]);
+        }
+        __syncthreads();
+        if (patch_live) {
+            for (int j0 = 0; j0 < cnt; j0 += 32) {
+                const int j = j0 + lane;
+                bool pass = false;
+                if (j < cnt) {
+                    const float4 A = sA[j];
+                    const float ry = sB[j].x;
+                    pass = (A.z >= 0.0f) && (A.x - A.w <= pat_x1) && (pat_x0 <= A.x + A.w) &&
+                           (A.y - ry <= pat_y1) && (pat_y0 <= A.y + ry) && (A.z <= thresh);
+                }
+                unsigned mask = __ballot_sync(FULL, pass);
+                bool inserted = false;
+                while (mask) {
+                    const int jj = j0 + __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const float4 A = sA[jj];
+                    const float4 Bv = sB[jj];
+                    const float dx = xf - A.x;
+                    const float dy = yf - A.y;
+                    // rasterize_points.cu:92-97 -- same expression tree for q as the reference
+                    const float qv = Bv.y * dx * dx + Bv.z * dx * dy + Bv.w * dy * dy;
+                    const float cut = PER_POINT_CUTOFF ? sCut[jj] : a.cutoff_uniform;
+                    const bool ok = valid && !(fabsf(dx) > A.w || fabsf(dy) > Bv.x) && !(qv > cut);
+                    if (ok) {
+                        const int id = sId[jj];
+                        const float z = A.z + 0.0f;  // canonicalise -0
+                        if (frag_less(z, id, fz[KMAX - 1], fid[KMAX - 1])) {
+                            inserted = true;
+#pragma unroll
+                            for (int i = KMAX - 1; i >= 0; --i) {
+                                if (frag_less(z, id, fz[i], fid[i])) {
+                                    const bool shift = (i > 0) && frag_less(z, id, fz[i > 0 ? i - 1 : 0],
+                                                                             fid[i > 0 ? i - 1 : 0]);
+                                    fz[i] = shift ? fz[i > 0 ? i - 1 : 0] : z;
+                                    fq[i] = shift ? fq[i > 0 ? i - 1 : 0] : qv;
+                                    fid[i] = shift ? fid[i > 0 ? i - 1 : 0] : id;
+                                }
+                            }
+                        }
+                    }
+                }
+                if (__any_sync(FULL, inserted)) {
+                    const float kz = valid ? fz[KMAX - 1] : -CUDART_INF_F;
+                    thresh = __int_as_float(__reduce_max_sync(FULL, __float_as_int(kz)));
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    if (!valid) return;
+    // ---- epilogue: depth merge, outputs (image row S-1-yi, col S-1-xi: rasterize_points.cu:577-580) ----
+    const int64_t pix = ((int64_t)n * S + (S - 1 - yi)) * S + (S - 1 - xi);
+    const bool any = fid[0] != INT32_MAX;
+    const float z0 = fz[0];
+    bool emit[KMAX];
+    bool open = any;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+        // rasterize_points.cu:586-595: stop at the first fragment farther than the merge threshold
+        open = open && (k < K) && (fid[k] != INT32_MAX) && !(fz[k] - z0 > a.depth_merge);
+        emit[k] = open;
+    }
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+        if (k < K) {
+            a.idx[pix * K + k] = emit[k] ? fid[k] : -1;
+            if (a.zbuf) a.zbuf[pix * K + k] = emit[k] ? fz[k] : -1.0f;
+            if (a.qvalue) a.qvalue[pix * K + k] = emit[k] ? fq[k] : -1.0f;
+        }
+    }
+    const float occ = any ? 1.0f : 0.0f;
+    if (a.occ) a.occ[pix] = occ;
+    if (BLEND) {
+        // renderer.py:53 w = exp(-0.5 q) * scaler ; norm_weighted_sum [ext]: sum w f / max(sum w, 1e-4)
+        float w[KMAX];
+        float wsum = 0.f, r = 0.f, g = 0.f, b = 0.f;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+            w[k] = 0.f;
+            if (emit[k]) {
+                const int id = fid[k];
+                w[k] = expf(-0.5f * fq[k]) * __ldg(&a.scaler[id]);
+                const float *c = a.colours + (int64_t)id * 3;
+                r += w[k] * __ldg(c + 0);
+                g += w[k] * __ldg(c + 1);
+                b += w[k] * __ldg(c + 2);
+                wsum += w[k];
+                if (a.visible) a.visible[id] = 1;
+            }
+        }
+        const float inv = 1.0f / fmaxf(wsum, 1e-4f);
+        reinterpret_cast<float4 *>(a.image)[pix] = make_float4(r * inv, g * inv, b * inv, occ);
+        if (a.weights) {
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k)
+                if (k < K) a.weights[pix * K + k] = w[k] * inv;
+        }
+    }
+}
+
+template <int KMAX>
+static int launch_raster(dss_ctx *ctx, const RasterArgs &a, cudaStream_t st) {
+    dim3 grid((unsigned)(a.B * a.B), (unsigned)a.N);
+    const bool blend = a.image != nullptr;
+    if (blend) {
+        if (a.cutoff)
+            raster_fwd_kernel<KMAX, true, true><<<grid, RASTER_THREADS, 0, st>>>(a);
+        else
+            raster_fwd_kernel<KMAX, false, true><<<grid, RASTER_THREADS, 0, st>>>(a);
+    } else {
+        if (a.cutoff)
+            raster_fwd_kernel<KMAX, true, false><<<grid, RASTER_THREADS, 0, st>>>(a);
+        else
+            raster_fwd_kernel<KMAX, false, false><<<grid, RASTER_THREADS, 0, st>>>(a);
+    }
+    DSS_LAUNCH_CHECK(ctx);
+    return DSS_OK;
+}
+
+int raster_forward(dss_ctx *ctx, const RasterArgs &a, cudaStream_t st) {
+    if (a.N <= 0 || a.S <= 0) return DSS_OK;
+    if (a.K <= 5) return launch_raster<5>(ctx, a, st);
+    if (a.K <= 8) return launch_raster<8>(ctx, a, st);
+    if (a.K <= 16) return launch_raster<16>(ctx, a, st);
+    return launch_raster<DSS_MAX_POINTS_PER_PIXEL>(ctx, a, st);
+}
+
+int bin_and_raster(dss_ctx *ctx, RasterArgs a, const int64_t *first_idx, const int64_t *num_points,
+                   int64_t P0, cudaStream_t st) {
+    const int S = a.S;
+    a.B = (S + RASTER_TILE - 1) / RASTER_TILE;
+    const int64_t nb = (int64_t)a.N * a.B * a.B;
+    if (nb + 1 >= (int64_t)INT32_MAX) {
+        set_error("too many tiles (%lld)", (long long)nb);
+        return DSS_E_INVALID;
+    }
+    int32_t *counts = nullptr, *offsets = nullptr, *ids = nullptr;
+    int rc;
+    if ((rc = ctx_get(ctx, BUF_TILE_COUNTS, (size_t)(nb + 1), &counts))) return rc;
+    if ((rc = ctx_get(ctx, BUF_TILE_OFFSETS, (size_t)(nb + 1), &offsets))) return rc;
+    if ((rc = bin_count_and_scan(ctx, a.rec, first_idx, num_points, a.N, P0, S, RASTER_TILE, counts, offsets, st)))
+        return rc;
+    // the one host round-trip of the forward pass: size of the CSR id list
+    DSS_CUDA_TRY(cudaMemcpyAsync(ctx->h_pinned, offsets + nb, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    DSS_CUDA_TRY(cudaStreamSynchronize(st));
+    const int64_t total = (int64_t)(*reinterpret_cast<int32_t *>(ctx->h_pinned));
+    if (total < 0) {
+        set_error("tile list size overflowed int32");
+        return DSS_E_INVALID;
+    }
+    if ((rc = ctx_get(ctx, BUF_TILE_IDS, (size_t)(total > 0 ? total : 1), &ids))) return rc;
+    if (total > 0)
+        if ((rc = bin_scatter(ctx, a.rec, first_idx, num_points, a.N, P0, S, RASTER_TILE, offsets, counts, ids, st)))
+            return rc;
+    a.tile_offsets = offsets;
+    a.tile_ids = ids;
+    return raster_forward(ctx, a, st);
+}
+
+}  // namespace dss
+
+extern "C" {
+
+int dss_splat_points(dss_ctx *ctx, const float *points, const float *ellipse_params, const float *cutoff_thres,
+                     const float *radii, const int64_t *first_idx, const int64_t *num_points, int N, int64_t P,
+                     float depth_merging_thres, int image_size, int points_per_pixel, int bin_size, int32_t *idx,
+                     float *zbuf, float *qvalue, float *occupancy, void *stream) {
+    using namespace dss;
+    (void)bin_size;
+    cudaStream_t st = (cudaStream_t)stream;
+    DSS_REQUIRE(ctx != nullptr, "ctx is null");
+    DSS_REQUIRE(N >= 0 && P >= 0, "negative size");
+    DSS_REQUIRE(image_size > 0, "image_size must be positive");
+    DSS_REQUIRE(points_per_pixel > 0 && points_per_pixel <= DSS_MAX_POINTS_PER_PIXEL,
+                "points_per_pixel must be in [1, 64]");
+    DSS_REQUIRE(P < (int64_t)INT32_MAX, "more than 2^31-1 packed points");
+    if (N == 0) return DSS_OK;
+    DSS_REQUIRE(idx && occupancy && first_idx && num_points, "null pointer");
+    DSS_REQUIRE(P == 0 || (points && ellipse_params && cutoff_thres && radii), "null input array");
+    float4 *rec = nullptr;
+    int rc;
+    if ((rc = ctx_get(ctx, BUF_RECORDS, (size_t)(2 * (P > 0 ? P : 1)), &rec))) return rc;
+    if ((rc = pack_records(ctx, points, radii, ellipse_params, P, rec, st))) return rc;
+    RasterArgs a;
+    memset(&a, 0, sizeof(a));
+    a.rec = rec;
+    a.cutoff = cutoff_thres;
+    a.cutoff_uniform = 0.f;
+    a.N = N;
+    a.S = image_size;
+    a.K = points_per_pixel;
+    a.depth_merge = depth_merging_thres;
+    a.idx = idx;
+    a.zbuf = zbuf;
+    a.qvalue = qvalue;
+    a.occ = occupancy;
+    return bin_and_raster(ctx, a, first_idx, num_points, P, st);
+}
+
+}  // extern "C"

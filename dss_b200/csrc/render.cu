@@ -1,0 +1,382 @@
+// render.cu -- fused renderer path: per-(point,view) preprocess, forward orchestration, backward
+// orchestration (gradient clip + chain to world space).
+#include <math_constants.h>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace dss {
+
+static inline unsigned int nblocks(int64_t items, int threads, int sm_count, int per_sm) {
+    int64_t b = (items + threads - 1) / threads;
+    const int64_t cap = (int64_t)sm_count * per_sm;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (unsigned int)b;
+}
+
+struct PreArgs {
+    const float *pts, *nrm, *proj, *view, *h;
+    const int64_t *first_idx, *num_points;
+    int64_t P0;
+    int shared_cloud, h_per_splat, S, backface;
+    float cutoffC, sigma, znear, zfar;
+    float4 *rec;
+    float *ndc, *ellipse, *radii, *scaler;
+};
+
+// Python-side eps helpers of the reference (DSS/utils/mathHelper.py:10-22), zero counts as positive.
+__device__ __forceinline__ float py_eps_denom(float d) { return eps_denom(d, 1e-17f); }
+__device__ __forceinline__ float py_eps_sqrt(float s) { return fmaxf(fabsf(s), 1e-17f); }
+
+// ---------------------------------------------------------------------------------------------
+// One thread per (view, point).  Fuses DSS/core/rasterizer.py:183-217 (depth filter), :148-181
+// (backface filter), :443-496 (_compute_WJk), :293-342 (global/isotropic Vrk with Sk^T Sk = I - n n^T),
+// :404-441 (variance + detMk), :525-565 (conic, radii, scaler) and the pytorch3d transform of :614
+// (x/t, y/t, view-space z) -- about 40 ATen launches incl. batched det/inverse in the reference.
+// Filtered points keep their slot but get z = -1, which every later stage treats as "not renderable"
+// exactly like the reference treats points behind the camera (rasterize_points.cu:87-88).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) preprocess_kernel(const __grid_constant__ PreArgs a) {
+    __shared__ float sM[16], sV[16];
+    const int n = blockIdx.y;
+    if (threadIdx.x < 16) {
+        sM[threadIdx.x] = a.proj[n * 16 + threadIdx.x];
+        sV[threadIdx.x] = a.view[n * 16 + threadIdx.x];
+    }
+    __syncthreads();
+    const ViewRange vr = view_range(a.shared_cloud ? nullptr : a.first_idx, a.num_points, n, a.P0);
+    const float pix = 2.0f / (float)a.S;
+    const float aa = a.sigma * pix * pix;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < vr.count;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t s = vr.first + i;                     // packed slot
+        const int64_t src = a.shared_cloud ? i : s;         // where the world-space point lives
+        const float p0 = a.pts[src * 3 + 0], p1 = a.pts[src * 3 + 1], p2 = a.pts[src * 3 + 2];
+        const float n0 = a.nrm[src * 3 + 0], n1 = a.nrm[src * 3 + 1], n2 = a.nrm[src * 3 + 2];
+        // [p 1] . M  (row-vector convention, rasterizer.py:465-476)
+        const float x = fmaf(p0, sM[0], fmaf(p1, sM[4], fmaf(p2, sM[8], sM[12])));
+        const float y = fmaf(p0, sM[1], fmaf(p1, sM[5], fmaf(p2, sM[9], sM[13])));
+        const float t = fmaf(p0, sM[3], fmaf(p1, sM[7], fmaf(p2, sM[11], sM[15])));
+        float zv = fmaf(p0, sV[2], fmaf(p1, sV[6], fmaf(p2, sV[10], sV[14])));
+        const float te = py_eps_denom(t);
+        const float t2 = py_eps_denom(t * t);
+        const float it = 1.0f / te, it2 = 1.0f / t2;
+        // J = d(ndc xy)/d(world xyz), 3x2 (Mk = W @ Jk, rasterizer.py:483-494)
+        float J0[3], J1[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            J0[k] = sM[k * 4 + 0] * it - sM[k * 4 + 3] * x * it2;
+            J1[k] = sM[k * 4 + 1] * it - sM[k * 4 + 3] * y * it2;
+        }
+        // T = J^T (I - n n^T) J
+        const float nj0 = n0 * J0[0] + n1 * J0[1] + n2 * J0[2];
+        const float nj1 = n0 * J1[0] + n1 * J1[1] + n2 * J1[2];
+        const float T00 = (J0[0] * J0[0] + J0[1] * J0[1] + J0[2] * J0[2]) - nj0 * nj0;
+        const float T01 = (J0[0] * J1[0] + J0[1] * J1[1] + J0[2] * J1[2]) - nj0 * nj1;
+        const float T11 = (J1[0] * J1[0] + J1[1] * J1[1] + J1[2] * J1[2]) - nj1 * nj1;
+        const float hh = a.h_per_splat ? a.h[s] : a.h[n];
+        const float G00 = fmaf(hh, T00, aa), G01 = hh * T01, G11 = fmaf(hh, T11, aa);
+        const float detG = G00 * G11 - G01 * G01;
+        const float idet = 1.0f / detG;
+        const float ea = G11 * idet, eb = -2.0f * G01 * idet, ec = G00 * idet;   // rasterizer.py:543-551
+        const float den = py_eps_denom(4.0f * ea * ec - eb * eb);                 // :509-519
+        const float ry = sqrtf(py_eps_sqrt(4.0f * ea * a.cutoffC / den));
+        const float rx = sqrtf(py_eps_sqrt(4.0f * ec * a.cutoffC / den));
+        const float detT = fmaxf(T00 * T11 - T01 * T01, 0.0f);
+        const float sc = sqrtf(detT) /
+                         py_eps_denom(sqrtf(py_eps_sqrt(detG * (4.0f * CUDART_PI_F * CUDART_PI_F))));  // :558-559
+        // filters (rasterizer.py:187-192, :152): view-space depth range, optional backface
+        bool keep = (zv >= a.znear) && (zv <= a.zfar);
+        if (a.backface) {
+            const float nz = n0 * sV[2] + n1 * sV[6] + n2 * sV[10];
+            keep = keep && (nz < 0.0f);
+        }
+        if (!keep) zv = -1.0f;
+        const float xn = x / t, yn = y / t;
+        a.rec[2 * s] = make_float4(xn, yn, zv, rx);
+        a.rec[2 * s + 1] = make_float4(ry, ea, eb, ec);
+        if (a.scaler) a.scaler[s] = sc;
+        if (a.ndc) {
+            a.ndc[s * 3 + 0] = xn;
+            a.ndc[s * 3 + 1] = yn;
+            a.ndc[s * 3 + 2] = zv;
+        }
+        if (a.ellipse) {
+            a.ellipse[s * 3 + 0] = ea;
+            a.ellipse[s * 3 + 1] = eb;
+            a.ellipse[s * 3 + 2] = ec;
+        }
+        if (a.radii) {
+            a.radii[s * 2 + 0] = rx;
+            a.radii[s * 2 + 1] = ry;
+        }
+    }
+}
+
+static int check_common(const dss_render_args *g) {
+    DSS_REQUIRE(g != nullptr, "args is null");
+    DSS_REQUIRE(g->n_views > 0, "n_views must be positive");
+    DSS_REQUIRE(g->P0 >= 0 && g->P >= 0, "negative size");
+    DSS_REQUIRE(g->P < (int64_t)INT32_MAX, "more than 2^31-1 packed points");
+    DSS_REQUIRE(g->image_size > 0, "image_size must be positive");
+    DSS_REQUIRE(g->points_per_pixel > 0 && g->points_per_pixel <= DSS_MAX_POINTS_PER_PIXEL,
+                "points_per_pixel must be in [1, 64]");
+    DSS_REQUIRE(g->shared_cloud || (g->first_idx && g->num_points), "first_idx/num_points required");
+    DSS_REQUIRE(!g->shared_cloud || g->P == (int64_t)g->n_views * g->P0, "P != n_views * P0");
+    return DSS_OK;
+}
+
+static int run_preprocess(dss_ctx *ctx, const dss_render_args *g, float4 *rec, cudaStream_t st) {
+    if (g->P == 0 || g->P0 == 0) return DSS_OK;
+    DSS_REQUIRE(g->points_world && g->normals_world && g->proj && g->view && g->h, "null input array");
+    PreArgs a;
+    a.pts = g->points_world;
+    a.nrm = g->normals_world;
+    a.proj = g->proj;
+    a.view = g->view;
+    a.h = g->h;
+    a.first_idx = g->first_idx;
+    a.num_points = g->num_points;
+    a.P0 = g->P0;
+    a.shared_cloud = g->shared_cloud;
+    a.h_per_splat = g->h_per_splat;
+    a.S = g->image_size;
+    a.backface = g->backface_culling;
+    a.cutoffC = g->cutoff_threshold;
+    a.sigma = g->antialiasing_sigma;
+    a.znear = g->znear;
+    a.zfar = g->zfar;
+    a.rec = rec;
+    a.ndc = g->ndc;
+    a.ellipse = g->ellipse;
+    a.radii = g->radii;
+    a.scaler = g->scaler;
+    dim3 grid(nblocks(g->P0, 256, ctx->sm_count, 8), g->n_views);
+    preprocess_kernel<<<grid, 256, 0, st>>>(a);
+    DSS_LAUNCH_CHECK(ctx);
+    return DSS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Backward tail: per-point gradient clip (rasterizer.py:667-673) and chain through
+// ndc = (X/T, Y/T, z_view) to world space: d ndc_xy / d p = J (the same Jacobian as the forward
+// pass), d z_view / d p = V[:3, 2].  shared_cloud: one thread per world point loops over the views
+// and writes the sum (deterministic, no atomics); otherwise one thread per packed splat.
+// ---------------------------------------------------------------------------------------------
+struct ChainArgs {
+    const float *pts, *proj, *view;
+    const float2 *gxy;     // (P,2) occupancy gradient
+    const float *gz;       // (P,) z gradient or null
+    const int64_t *first_idx, *num_points;
+    int64_t P0;
+    int N, shared_cloud;
+    float clip;
+    float *grad_ndc;       // (P,3) or null
+    float *grad_world;     // (P0,3) or (P,3)
+};
+
+__device__ __forceinline__ void chain_one(const float *M, const float *V, float p0, float p1, float p2,
+                                          float gx, float gy, float gz, float &w0, float &w1, float &w2) {
+    const float x = fmaf(p0, M[0], fmaf(p1, M[4], fmaf(p2, M[8], M[12])));
+    const float y = fmaf(p0, M[1], fmaf(p1, M[5], fmaf(p2, M[9], M[13])));
+    const float t = fmaf(p0, M[3], fmaf(p1, M[7], fmaf(p2, M[11], M[15])));
+    const float it = 1.0f / t, it2 = it * it;
+    float w[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float j0 = M[k * 4 + 0] * it - M[k * 4 + 3] * x * it2;
+        const float j1 = M[k * 4 + 1] * it - M[k * 4 + 3] * y * it2;
+        w[k] = j0 * gx + j1 * gy + V[k * 4 + 2] * gz;
+    }
+    w0 = w[0];
+    w1 = w[1];
+    w2 = w[2];
+}
+
+__device__ __forceinline__ void clip_grad(float clip, float &gx, float &gy, float &gz) {
+    if (clip > 0.0f) {
+        // grad.norm().clamp(0, clip) * normalize(grad)  (F.normalize eps = 1e-12)
+        const float nrm = sqrtf(gx * gx + gy * gy + gz * gz);
+        const float s = fminf(nrm, clip) / fmaxf(nrm, 1e-12f);
+        gx *= s;
+        gy *= s;
+        gz *= s;
+    }
+}
+
+__global__ void __launch_bounds__(256) chain_kernel(const __grid_constant__ ChainArgs a) {
+    extern __shared__ float sMat[];  // N * 32 floats: proj then view per view (shared_cloud) or 32 (packed)
+    if (a.shared_cloud) {
+        for (int i = threadIdx.x; i < a.N * 16; i += blockDim.x) {
+            sMat[(i / 16) * 32 + (i % 16)] = a.proj[i];
+            sMat[(i / 16) * 32 + 16 + (i % 16)] = a.view[i];
+        }
+        __syncthreads();
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.P0;
+             i += (int64_t)gridDim.x * blockDim.x) {
+            const float p0 = a.pts[i * 3], p1 = a.pts[i * 3 + 1], p2 = a.pts[i * 3 + 2];
+            float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
+            for (int n = 0; n < a.N; ++n) {
+                const int64_t s = (int64_t)n * a.P0 + i;
+                const float2 g = a.gxy[s];
+                float gx = g.x, gy = g.y, gz = a.gz ? a.gz[s] : 0.0f;
+                clip_grad(a.clip, gx, gy, gz);
+                if (a.grad_ndc) {
+                    a.grad_ndc[s * 3 + 0] = gx;
+                    a.grad_ndc[s * 3 + 1] = gy;
+                    a.grad_ndc[s * 3 + 2] = gz;
+                }
+                if (gx != 0.0f || gy != 0.0f || gz != 0.0f) {
+                    float w0, w1, w2;
+                    chain_one(sMat + n * 32, sMat + n * 32 + 16, p0, p1, p2, gx, gy, gz, w0, w1, w2);
+                    acc0 += w0;
+                    acc1 += w1;
+                    acc2 += w2;
+                }
+            }
+            a.grad_world[i * 3 + 0] = acc0;
+            a.grad_world[i * 3 + 1] = acc1;
+            a.grad_world[i * 3 + 2] = acc2;
+        }
+    } else {
+        const int n = blockIdx.y;
+        if (threadIdx.x < 16) {
+            sMat[threadIdx.x] = a.proj[n * 16 + threadIdx.x];
+            sMat[16 + threadIdx.x] = a.view[n * 16 + threadIdx.x];
+        }
+        __syncthreads();
+        const ViewRange vr = view_range(a.first_idx, a.num_points, n, a.P0);
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < vr.count;
+             i += (int64_t)gridDim.x * blockDim.x) {
+            const int64_t s = vr.first + i;
+            const float2 g = a.gxy[s];
+            float gx = g.x, gy = g.y, gz = a.gz ? a.gz[s] : 0.0f;
+            clip_grad(a.clip, gx, gy, gz);
+            if (a.grad_ndc) {
+                a.grad_ndc[s * 3 + 0] = gx;
+                a.grad_ndc[s * 3 + 1] = gy;
+                a.grad_ndc[s * 3 + 2] = gz;
+            }
+            float w0 = 0.f, w1 = 0.f, w2 = 0.f;
+            if (gx != 0.0f || gy != 0.0f || gz != 0.0f)
+                chain_one(sMat, sMat + 16, a.pts[s * 3], a.pts[s * 3 + 1], a.pts[s * 3 + 2], gx, gy, gz, w0, w1, w2);
+            a.grad_world[s * 3 + 0] = w0;
+            a.grad_world[s * 3 + 1] = w1;
+            a.grad_world[s * 3 + 2] = w2;
+        }
+    }
+}
+
+}  // namespace dss
+
+extern "C" {
+
+int dss_preprocess(dss_ctx *ctx, const dss_render_args *g, void *stream) {
+    using namespace dss;
+    DSS_REQUIRE(ctx != nullptr, "ctx is null");
+    int rc = check_common(g);
+    if (rc) return rc;
+    float4 *rec = reinterpret_cast<float4 *>(g->records);
+    if (!rec && (rc = ctx_get(ctx, BUF_RECORDS, (size_t)(2 * (g->P > 0 ? g->P : 1)), &rec))) return rc;
+    return run_preprocess(ctx, g, rec, (cudaStream_t)stream);
+}
+
+int dss_render_forward(dss_ctx *ctx, const dss_render_args *g, void *stream) {
+    using namespace dss;
+    cudaStream_t st = (cudaStream_t)stream;
+    DSS_REQUIRE(ctx != nullptr, "ctx is null");
+    int rc = check_common(g);
+    if (rc) return rc;
+    DSS_REQUIRE(g->image && g->idx && g->scaler && g->colours, "forward needs image, idx, scaler, colours");
+    float4 *rec = reinterpret_cast<float4 *>(g->records);
+    if (!rec && (rc = ctx_get(ctx, BUF_RECORDS, (size_t)(2 * (g->P > 0 ? g->P : 1)), &rec))) return rc;
+    DSS_REQUIRE((reinterpret_cast<uintptr_t>(rec) & 15) == 0, "records must be 16-byte aligned");
+    if ((rc = run_preprocess(ctx, g, rec, st))) return rc;
+    if (g->visible) DSS_CUDA_TRY(cudaMemsetAsync(g->visible, 0, (size_t)g->P, st));
+    RasterArgs a;
+    memset(&a, 0, sizeof(a));
+    a.rec = rec;
+    a.cutoff = nullptr;
+    a.cutoff_uniform = g->cutoff_threshold;
+    a.N = g->n_views;
+    a.S = g->image_size;
+    a.K = g->points_per_pixel;
+    a.depth_merge = g->depth_merging_threshold;
+    a.idx = g->idx;
+    a.zbuf = g->zbuf;
+    a.qvalue = g->qvalue;
+    a.occ = nullptr;
+    a.scaler = g->scaler;
+    a.colours = g->colours;
+    a.image = g->image;
+    a.weights = g->weights;
+    a.visible = g->visible;
+    return bin_and_raster(ctx, a, g->shared_cloud ? nullptr : g->first_idx, g->num_points, g->P0, st);
+}
+
+int dss_render_backward(dss_ctx *ctx, const dss_render_args *g, void *stream) {
+    using namespace dss;
+    cudaStream_t st = (cudaStream_t)stream;
+    DSS_REQUIRE(ctx != nullptr, "ctx is null");
+    int rc = check_common(g);
+    if (rc) return rc;
+    DSS_REQUIRE(g->grad_image && g->idx && g->weights && g->visible, "backward needs grad_image, idx, weights, visible");
+    DSS_REQUIRE(g->records || (g->ndc && g->radii), "backward needs the records (or ndc and radii) saved by the forward pass");
+    DSS_REQUIRE(g->grad_points_world && g->points_world && g->proj && g->view, "null pointer");
+    const int N = g->n_views, S = g->image_size, K = g->points_per_pixel;
+    const int64_t P = g->P, npix = (int64_t)N * S * S;
+    const int64_t *fi = g->shared_cloud ? nullptr : g->first_idx;
+    if (P == 0) return DSS_OK;
+    float4 *rec = reinterpret_cast<float4 *>(g->records);
+    float *rs = nullptr, *gxy = nullptr;
+    if (!rec) {
+        // rebuild from the tensors the caller saved (another forward may have reused the scratch)
+        if ((rc = ctx_get(ctx, BUF_RECORDS, (size_t)(2 * P), &rec))) return rc;
+        if ((rc = pack_records(ctx, g->ndc, g->radii, nullptr, P, rec, st))) return rc;
+    }
+    if ((rc = ctx_get(ctx, BUF_RS, (size_t)N, &rs))) return rc;
+    if ((rc = ctx_get(ctx, BUF_GRADXY, (size_t)(2 * P), &gxy))) return rc;
+    if ((rc = search_radius(ctx, rec, nullptr, g->visible, fi, g->num_points, N, g->P0, g->radii_backward_scaler,
+                            rs, st)))
+        return rc;
+    if (g->search_radius)
+        DSS_CUDA_TRY(cudaMemcpyAsync(g->search_radius, rs, (size_t)N * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if ((rc = occ_backward(ctx, rec, g->visible, rs, g->grad_image, 4, 3, fi, g->num_points, N, g->P0, S, gxy, st)))
+        return rc;
+    if (g->grad_colours) {
+        DSS_CUDA_TRY(cudaMemsetAsync(g->grad_colours, 0, (size_t)P * 3 * sizeof(float), st));
+        if ((rc = colour_backward(ctx, g->idx, g->weights, g->grad_image, npix, K, g->grad_colours, st))) return rc;
+    }
+    float *gz = nullptr;
+    if (g->grad_zbuf) {
+        if ((rc = ctx_get(ctx, BUF_MISC, (size_t)P, &gz))) return rc;
+        DSS_CUDA_TRY(cudaMemsetAsync(gz, 0, (size_t)P * sizeof(float), st));
+        if ((rc = zbuf_backward(ctx, g->idx, g->grad_zbuf, npix, K, gz, 1, st))) return rc;
+    }
+    ChainArgs c;
+    c.pts = g->points_world;
+    c.proj = g->proj;
+    c.view = g->view;
+    c.gxy = reinterpret_cast<const float2 *>(gxy);
+    c.gz = gz;
+    c.first_idx = fi;
+    c.num_points = g->num_points;
+    c.P0 = g->P0;
+    c.N = N;
+    c.shared_cloud = g->shared_cloud;
+    c.clip = g->clip_pts_grad;
+    c.grad_ndc = g->grad_ndc;
+    c.grad_world = g->grad_points_world;
+    if (g->shared_cloud) {
+        DSS_REQUIRE(N <= 256, "shared-cloud backward supports at most 256 views per call");
+        chain_kernel<<<nblocks(g->P0, 256, ctx->sm_count, 8), 256, (size_t)N * 32 * sizeof(float), st>>>(c);
+    } else {
+        dim3 grid(nblocks(g->P0, 256, ctx->sm_count, 8), N);
+        chain_kernel<<<grid, 256, 32 * sizeof(float), st>>>(c);
+    }
+    DSS_LAUNCH_CHECK(ctx);
+    return DSS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,205 @@
+/*
+ * dss_b200.h -- C ABI of the B200-native surface-splatting rasterizer (libdss_b200.so).
+ *
+ * This is the drop-in boundary for ONE hot path of yifita/DSS: the elliptical point rasterizer,
+ * forward and backward.  Every entry point is `extern "C"`, takes raw DEVICE pointers (unless a
+ * parameter is explicitly marked host), sizes, and a cudaStream_t passed as void*; it enqueues
+ * work on that stream and returns an int status (DSS_OK or a negative DSS_E_* code, never a C++
+ * exception).  dss_last_error() returns a thread-local description of the last failure.
+ *
+ * The reference interfaces each entry point replaces are cited as <file>:<line> relative to the
+ * yifita/DSS checkout (reference commit 8fd8d86).  Reference-side bindings: INTEGRATION.md.
+ *
+ * Conventions shared with the reference:
+ *   - "packed" arrays hold all N views back to back: view n owns rows
+ *     [first_idx[n], first_idx[n] + num_points[n]); first_idx / num_points are int64 DEVICE arrays
+ *     exactly as DSS._C receives them (DSS/csrc/rasterize_points.h:461-472);
+ *   - points are NDC x,y in [-1,1] (+X left, +Y up) and view-space depth z; points with z < 0 are
+ *     never rasterized (DSS/csrc/rasterize_points.cu:87-88);
+ *   - output pixel (row r, col c) is the NDC pixel (S-1-r, S-1-c) (rasterize_points.cu:577-580);
+ *   - idx / zbuf / qvalue are (N,S,S,K), -1 padded; occupancy (N,S,S) is 0/1 float.
+ */
+#ifndef DSS_B200_H
+#define DSS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define DSS_API __attribute__((visibility("default")))
+#else
+#define DSS_API
+#endif
+
+#define DSS_OK 0
+#define DSS_E_INVALID -1    /* bad argument (null pointer, size out of range, K too large ...) */
+#define DSS_E_CUDA -2       /* a CUDA runtime call or kernel launch failed                    */
+#define DSS_E_NOMEM -3      /* scratch allocation failed                                      */
+#define DSS_E_CAPACITY -4   /* caller-provided output capacity too small (see *_required)     */
+
+#define DSS_MAX_POINTS_PER_PIXEL 64   /* reference allows 150 (rasterization_utils.cuh:18); configs use 5 / 8 */
+
+typedef struct dss_ctx dss_ctx;   /* owns grow-only device scratch for one device; not thread-safe */
+
+/* ---- library / context ------------------------------------------------------------------- */
+DSS_API int dss_version(void);                       /* ABI version, currently 1                        */
+DSS_API const char *dss_last_error(void);            /* thread-local message for the last DSS_E_* return */
+DSS_API int dss_create(dss_ctx **out);               /* bind to the CURRENT cuda device                  */
+DSS_API void dss_destroy(dss_ctx *ctx);
+DSS_API size_t dss_scratch_bytes(const dss_ctx *ctx);/* device bytes currently held by the context       */
+/* number of kernels the library has launched on this context since creation (bench: gpu_launches) */
+DSS_API int64_t dss_launch_count(const dss_ctx *ctx);
+
+/* ---- exclusive prefix sum -----------------------------------------------------------------
+ * Replaces prefix_sum.prefix_sum_cuda(grid_cnt, num_grids, grid_off)
+ * (external/prefix_sum/prefix_sum.h:6-21, prefix_sum.cu:74-87,135-205): exclusive int32 scan of the
+ * first n elements of `in` into `out` (in == out allowed).  Single pass, decoupled look-back; no
+ * allocation, no device synchronisation. */
+DSS_API int dss_exclusive_scan_i32(dss_ctx *ctx, const int32_t *in, int32_t *out, int64_t n, void *stream);
+
+/* ---- 2-D radius binning (uniform grid) ----------------------------------------------------
+ * Replace frnn._C.insert_points_cuda / counting_sort_cuda for D = 2
+ * (external/FRNN/frnn/csrc/grid/grid.h:43-50, grid.cu:62-99,144-200;
+ *  counting_sort.h:4-11, counting_sort.cu:5-36,72-135).
+ * points (N,Pmax,2) f32 padded; lengths (N,) i64; params (N,6) f32 = min_x,min_y,1/cell,res_x,res_y,total;
+ * grid_cnt (N,G) i32 must be zero on entry; grid_cell, grid_idx (N,Pmax) i32. */
+DSS_API int dss_grid_insert_points_2d(dss_ctx *ctx, const float *points, const int64_t *lengths,
+                              const float *params, int32_t *grid_cnt, int32_t *grid_cell,
+                              int32_t *grid_idx, int N, int Pmax, int G, void *stream);
+DSS_API int dss_grid_counting_sort_2d(dss_ctx *ctx, const float *points, const int64_t *lengths,
+                              const int32_t *grid_cell, const int32_t *grid_idx,
+                              const int32_t *grid_off, float *sorted_points, int32_t *sorted_idx,
+                              int N, int Pmax, int G, void *stream);
+
+/* ---- coarse rasterization (screen-tile binning) -------------------------------------------
+ * Replaces _C._rasterize_coarse(points, radii, first_idx, num, image_size, bin_size, M)
+ * (DSS/csrc/ext.cpp:11; rasterize_points.h:167-203; rasterize_points.cu:293-500).
+ * The reference returns a dense (N,B,B,M) int32 tensor (M = max(1e4,P): 8 GB at 1M points); this
+ * returns the same bin membership as CSR: bin_offsets (N*B*B + 1) int32 exclusive offsets and
+ * bin_ids, the packed point ids of every bin (order inside a bin unspecified, as in the reference).
+ * B = 1 + (S-1)/bin_size; bin (by,bx) of view n is entry (n*B + by)*B + bx, in NDC-index space like
+ * the reference.  The overlap predicate is the reference's closed fp32 test (rasterize_points.cu:355-383)
+ * evaluated with the identical expression sequence, so membership is bit-exact.
+ * If the total exceeds bin_ids_capacity nothing is written to bin_ids, *total_required_host receives
+ * the needed size and DSS_E_CAPACITY is returned (call again).  Synchronises the stream once (the
+ * total is read back to size the id list, like the reference's host-side `at::full`). */
+DSS_API int dss_rasterize_coarse(dss_ctx *ctx, const float *points, const float *radii,
+                         const int64_t *first_idx, const int64_t *num_points, int N, int64_t P,
+                         int image_size, int bin_size, int32_t *bin_offsets, int32_t *bin_ids,
+                         int64_t bin_ids_capacity, int64_t *total_required_host, void *stream);
+
+/* ---- forward rasterization ----------------------------------------------------------------
+ * Replaces _C.splat_points(points, ellipse_params, cutoff_thres, radii, first_idx, num_points,
+ *                          depth_merging_thres, image_size, points_per_pixel, bin_size, max_points_per_bin)
+ * (DSS/csrc/ext.cpp:8; rasterize_points.h:461-525 -> RasterizePointsCoarse + RasterizePointsFine,
+ *  rasterize_points.cu:293-432,506-597; CheckPixelInsidePoint :64-124).
+ * Per pixel: among points of the view with z >= 0, |dx| <= rx, |dy| <= ry and
+ * q = a dx^2 + b dx dy + c dy^2 <= cutoff, keep the K with smallest (z, id), ascending; emit while
+ * z_k - z_0 <= depth_merging_thres.  `bin_size` is accepted for signature parity and ignored (tiling
+ * is internal); max_points_per_bin does not exist here (lists are exact-size CSR).
+ * zbuf / qvalue may be NULL (not written).  All outputs are fully written (no pre-fill needed). */
+DSS_API int dss_splat_points(dss_ctx *ctx, const float *points, const float *ellipse_params,
+                     const float *cutoff_thres, const float *radii, const int64_t *first_idx,
+                     const int64_t *num_points, int N, int64_t P, float depth_merging_thres,
+                     int image_size, int points_per_pixel, int bin_size, int32_t *idx, float *zbuf,
+                     float *qvalue, float *occupancy, void *stream);
+
+/* ---- backward: visibility, search radius, occupancy / z / colour gradients ------------------ */
+
+/* visible[p] = 1 iff p appears in idx at a pixel whose idx[...,0] >= 0
+ * (DSS/core/rasterizer.py:854-860; DSS/utils/__init__.py:320-340 -- replaces two torch.unique calls). */
+DSS_API int dss_visibility_from_idx(dss_ctx *ctx, const int32_t *idx, int64_t num_pixels, int K, int64_t P,
+                            uint8_t *visible, void *stream);
+
+/* rs[n] = radii_s * lower_median(flattened (rx,ry) of the view's visible points); 0 if none
+ * (DSS/core/rasterizer.py:888 -- replaces a per-view host loop with .item() syncs).  Exact radix select. */
+DSS_API int dss_search_radius(dss_ctx *ctx, const float *radii, const uint8_t *visible,
+                      const int64_t *first_idx, const int64_t *num_points, int N, int64_t P,
+                      float radii_s, float *rs, void *stream);
+
+/* Occupancy ("fast") backward.  Replaces the whole fast branch of EllipticalRasterizer.backward
+ * (DSS/core/rasterizer.py:845-972): visibility compaction, FRNN grid build, per-view prefix sums,
+ * counting sort, _C._splat_points_occ_fast_cuda_backward (rasterize_points_backward.cu:30-212,227-322)
+ * and the un-sort / scatter, by one gather kernel: for every visible point of view n,
+ *   grad_xy[p] = sum over pixels with g != 0, d2 <= rs[n]^2, not (g > 0 and outside bbox)
+ *                of (dx,dy) / eps_denom(d2,1e-10) * g .
+ * grad_occ is read as grad_occ[(n*S*S + r*S + c) * pix_stride + pix_offset] so that either a dense
+ * (N,S,S) map (stride 1, offset 0) or the alpha channel of an (N,S,S,4) image gradient (4, 3) can be
+ * passed.  grad_xy: (P,2), fully written (zeros for invisible points).  Deterministic (no atomics). */
+DSS_API int dss_occ_backward(dss_ctx *ctx, const float *points, const float *radii, const uint8_t *visible,
+                     const float *rs, const float *grad_occ, int pix_stride, int pix_offset,
+                     const int64_t *first_idx, const int64_t *num_points, int N, int64_t P,
+                     int image_size, float *grad_xy, void *stream);
+
+/* z_grad[idx_k] += grad_zbuf_k until the first idx < 0.  Replaces _C._backward_zbuf
+ * (DSS/csrc/ext.cpp:17; rasterize_points.h:388-419; rasterize_points.cu:823-885).  z_grad (P,) in-place. */
+DSS_API int dss_zbuf_backward(dss_ctx *ctx, const int32_t *idx, const float *grad_zbuf, int64_t num_pixels,
+                      int K, float *z_grad, void *stream);
+
+/* ---- fused renderer path (what bench.py times) ----------------------------------------------
+ * One call per direction for SurfaceSplattingRenderer.forward / its autograd backward
+ * (DSS/core/renderer.py:36-82, DSS/core/rasterizer.py:584-664,749-977).  All pointers device. */
+typedef struct dss_render_args {
+    /* geometry: `shared_cloud` != 0 -> points/normals are (P0,3), every view renders the same P0 points
+     * (the `extend`ed cloud of rasterizer.py:236-240) and first_idx/num_points are ignored;
+     * otherwise packed (P,3) with first_idx/num_points as above. */
+    const float *points_world;     /* (P0,3) or (P,3)                                            */
+    const float *normals_world;    /* same shape, unit length                                    */
+    const float *colours;          /* (P,3) per (view,point) features, e.g. shaded rgb            */
+    const float *proj;             /* (N,4,4) full projection, row-vector convention [x y z 1] M  */
+    const float *view;             /* (N,4,4) world-to-view, same convention                      */
+    const float *h;                /* (N,) variance scale per view, or (P,) per splat             */
+    const int64_t *first_idx;      /* (N,) or NULL when shared_cloud                              */
+    const int64_t *num_points;     /* (N,) or NULL when shared_cloud                              */
+    int32_t n_views;
+    int32_t shared_cloud;
+    int64_t P0;                    /* points per view when shared_cloud, else max points per view */
+    int64_t P;                     /* packed total (n_views * P0 when shared_cloud)               */
+    int32_t h_per_splat;
+    int32_t image_size;            /* S                                                           */
+    int32_t points_per_pixel;      /* K                                                           */
+    int32_t backface_culling;      /* rasterizer.py:148-181                                       */
+    float cutoff_threshold;        /* C   (rasterizer.py:522)                                     */
+    float depth_merging_threshold;
+    float antialiasing_sigma;
+    float znear, zfar;             /* depth filter (rasterizer.py:183-217)                        */
+    float radii_backward_scaler;   /* radii_s                                                     */
+    float clip_pts_grad;           /* <= 0: no clipping (rasterizer.py:667-673,735-736)           */
+    /* forward outputs / backward inputs, all caller-allocated */
+    float *records;                /* (P,8) packed splat records {x,y,z,rx, ry,a,b,c}: written by the
+                                      forward pass, read by the backward pass; 16-byte aligned.  May
+                                      be NULL (scratch is used; backward then rebuilds from ndc/radii) */
+    float *ndc;                    /* (P,3) x,y NDC, z view depth; z = -1 for filtered points; may be NULL */
+    float *ellipse;                /* (P,3) a,b,c; may be NULL                                     */
+    float *radii;                  /* (P,2); may be NULL                                           */
+    float *scaler;                 /* (P,)                                                         */
+    float *image;                  /* (N,S,S,4) rgb + occupancy                                   */
+    int32_t *idx;                  /* (N,S,S,K)                                                    */
+    float *weights;                /* (N,S,S,K) normalised blend weights w_k / max(sum w, 1e-4)    */
+    float *zbuf;                   /* (N,S,S,K) or NULL                                            */
+    float *qvalue;                 /* (N,S,S,K) or NULL                                            */
+    uint8_t *visible;              /* (P,)                                                         */
+    /* backward */
+    const float *grad_image;       /* (N,S,S,4)                                                    */
+    const float *grad_zbuf;        /* (N,S,S,K) or NULL                                            */
+    float *grad_colours;           /* (P,3)                                                        */
+    float *grad_ndc;               /* (P,3) gradient w.r.t. ndc (after clipping)                   */
+    float *grad_points_world;      /* (P0,3) summed over views when shared_cloud, else (P,3)       */
+    float *search_radius;          /* (N,) out                                                     */
+} dss_render_args;
+
+/* preprocess -> bin -> rasterize + blend.  Synchronises the stream once (tile-list size). */
+DSS_API int dss_render_forward(dss_ctx *ctx, const dss_render_args *args, void *stream);
+/* visibility/median radius -> occupancy gather -> colour scatter -> z scatter -> clip -> world chain. */
+DSS_API int dss_render_backward(dss_ctx *ctx, const dss_render_args *args, void *stream);
+/* per-(point,view) preprocess only (rasterizer.py:443-565 fused): writes ndc, ellipse, radii, scaler. */
+DSS_API int dss_preprocess(dss_ctx *ctx, const dss_render_args *args, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSS_B200_H */
