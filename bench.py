@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""bench.py -- forward+backward splat throughput of the surface-splatting hot path.
+
+    python bench.py --gpus 1 --steps 20 --warmup 3            # our arm, one JSON line
+    torchrun ... bench.py --gpus N ...                         # view-sharded, one rank per GPU (weak scaling)
+    python bench.py --impl reference ...                       # the reference's own CPU rasterizer (oracle/_ref)
+
+Metric (BASELINE.json): Msplats/s forward+backward, 1 splat = one (point, view) pair, on a synthetic
+1 M-point cloud rendered at 512x512, V views per GPU.  A "step" is one pass of the whole hot path
+[preprocess -> binning -> raster+blend -> injected image gradient -> colour/occupancy backward ->
+world-space gradients] over one batch of V views.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+BYTES_PER_SPLAT_FMT = "108*P0 + (32+8K)*S^2 per view"
+
+
+def algorithmic_bytes_per_view(P0, S, K):
+    """compulsory traffic of one view, forward+backward."""
+    return 108 * P0 + (32 + 8 * K) * S * S
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--points", type=int, default=1_000_000)
+    ap.add_argument("--image-size", type=int, default=512)
+    ap.add_argument("--views-per-gpu", type=int, default=8)
+    ap.add_argument("--k", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-sample-points", type=int, default=20000)
+    return ap.parse_args()
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's own CPU rasterizer compiled from its sources (oracle/_ref)
+# ------------------------------------------------------------------------------------------------
+def _cpu_sample_inputs(P_sample, S, K, seed=0):
+    """Screen-space inputs of ONE view of the bench workload, subsampled to P_sample points.  The CPU
+    preprocess uses the float64 oracle (no GPU needed); only the rasterizer fwd+bwd is timed, which is
+    what the reference's native CPU path covers (its Python layer cannot run without pytorch3d)."""
+    import numpy as np
+    import torch
+    import oracle
+    from tests.util import scene
+    pts, nrm, col, proj, view, _ = scene(P_sample, 1, seed=seed)
+    h = np.full((1,), 5e-5, np.float32)
+    pre = oracle.preprocess_f64(proj.numpy(), view.numpy(), pts.numpy(), nrm.numpy(), h, 1.0, 1.0, S)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+    g = torch.Generator().manual_seed(77)
+    return dict(points=t(pre["ndc"]), ellipse=t(pre["ellipse"]), radii=t(pre["radii"]),
+                cutoff=torch.ones(P_sample), first=torch.zeros(1, dtype=torch.int64),
+                num=torch.full((1,), P_sample, dtype=torch.int64),
+                grad_occ=torch.randn(1, S, S, generator=g) * 1e-3)
+
+
+def _cpu_one_view(args):
+    """Time the reference CPU fwd (+ occupancy backward) on one sampled view; returns seconds."""
+    P_sample, S, K, seed, radii_s = args
+    import torch
+    torch.set_num_threads(1)
+    from oracle import build_ref
+    ref = build_ref.ref_cpu()
+    x = _cpu_sample_inputs(P_sample, S, K, seed)
+    t0 = time.perf_counter()
+    if ref is not None:
+        # the reference's production path for this size: coarse + fine with the bin-size heuristic
+        # (rasterizer.py:713-722) and M = max(10000, P) (rasterizer.py:732-733)
+        bin_size = 8 if S <= 64 else 16 if S <= 256 else 32 if S <= 512 else 64
+        bins = ref.rasterize_coarse_cpu(x["points"], x["radii"], x["first"], x["num"], S, bin_size,
+                                        max(10000, P_sample))
+        ref.rasterize_fine_cpu(x["points"], x["ellipse"], x["cutoff"], x["radii"], bins, 0.05, S, bin_size, K)
+        ref.splat_points_occ_backward_cpu(x["points"], x["radii"], x["grad_occ"], x["first"], x["num"],
+                                          radii_s, 0.05)
+        kind = "reference"
+    else:
+        import oracle
+        idx, _, _, _ = oracle.splat_points_binned(x["points"].numpy(), x["ellipse"].numpy(), x["cutoff"].numpy(),
+                                                  x["radii"].numpy(), x["first"].numpy(), x["num"].numpy(), 0.05,
+                                                  S, K, 32)
+        vis = oracle.visibility(idx, P_sample)
+        rs = oracle.search_radius(x["radii"].numpy(), vis, x["first"].numpy(), x["num"].numpy(), radii_s)
+        oracle.occ_backward_fast(x["points"].numpy(), x["radii"].numpy(), vis, rs, x["grad_occ"].numpy(),
+                                 x["first"].numpy(), x["num"].numpy())
+        kind = "port"
+    return time.perf_counter() - t0, kind
+
+
+def cpu_baseline(P_sample, S, K, procs, views, radii_s=5.0):
+    """Msplats/s of the reference CPU rasterizer fwd+bwd on `views` sampled views spread over `procs`
+    single-threaded processes (the reference CPU code has no threading: SURVEY.md section 8d)."""
+    import multiprocessing as mp
+    jobs = [(P_sample, S, K, i, radii_s) for i in range(views)]
+    t0 = time.perf_counter()
+    if procs <= 1:
+        res = [_cpu_one_view(j) for j in jobs]
+    else:
+        with mp.get_context("spawn").Pool(procs) as pool:
+            res = pool.map(_cpu_one_view, jobs)
+    wall = time.perf_counter() - t0
+    kind = res[0][1]
+    return {"value": views * P_sample / wall / 1e6, "unit": "Msplats/s", "cores": procs, "kind": kind,
+            "sample": "%d view(s) x %d points subsampled from the bench cloud at %dx%d, K=%d: reference "
+                      "RasterizePointsCoarseCpu+FineCpu forward + RasterizePointsOccBackwardCpu (radii_s=%g), "
+                      "screen-space inputs precomputed; %.1f s wall" % (views, P_sample, S, S, K, radii_s, wall),
+            "seconds": wall}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 32))
+    P_sample, S, K = a.cpu_sample_points, a.image_size, a.k
+    times = []
+    for step in range(a.warmup + a.steps):
+        if step < a.warmup and step > 0:
+            continue                      # one warm-up pass is enough to page the module in
+        r = cpu_baseline(P_sample, S, K, procs, procs)
+        if step >= a.warmup:
+            times.append(r)
+        if sum(t["seconds"] for t in times) > 150:   # keep the whole run within a few minutes
+            break
+    wall = sum(t["seconds"] for t in times)
+    value = len(times) * procs * P_sample / wall / 1e6
+    line = {
+        "impl": "reference", "metric": "Msplats/s fwd+bwd", "value": value, "unit": "Msplats/s",
+        "n_gpus": a.gpus, "steps": len(times), "warmup": min(a.warmup, 1), "ms_per_step": 1e3 * wall / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "synthetic sphere %d pts x %d views/GPU, %dx%d, K=%d, fwd+bwd"
+                               % (a.points, a.views_per_gpu, S, S, K)},
+        "cpu_baseline": {"value": value, "unit": "Msplats/s", "cores": procs, "kind": times[0]["kind"],
+                         "sample": times[0]["sample"]},
+        "e2e": {"value": value, "unit": "Msplats/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from dss_b200 import _lib
+    from dss_b200.ops import SplatParams, render_points
+    from tests.util import sphere_cloud, random_cameras
+    from dss_b200.core.camera import camera_matrices
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (our arm) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    P0, S, K, V = a.points, a.image_size, a.k, a.views_per_gpu
+    prm = SplatParams(image_size=S, points_per_pixel=K, cutoff_threshold=1.0, depth_merging_threshold=0.05,
+                      antialiasing_sigma=1.0, radii_backward_scaler=5.0, clip_pts_grad=0.05,
+                      backface_culling=False, znear=0.1, zfar=100.0)            # configs/dss.yml:14-22
+    pts, nrm, col = sphere_cloud(P0, seed=0)
+    cams = random_cameras(V * world, seed=0)
+    proj_all, view_all = camera_matrices(cams)
+    sl = slice(rank * V, (rank + 1) * V)                       # this rank's contiguous slice of the views
+    proj_h, view_h = proj_all[sl].contiguous().pin_memory(), view_all[sl].contiguous().pin_memory()
+    g = torch.Generator().manual_seed(99 + rank)
+    colours_h = (col.repeat(V, 1) * (0.5 + 0.5 * torch.rand(V * P0, 1, generator=g))).pin_memory()
+    grad_h = (torch.randn(V, S, S, 4, generator=g) * 1e-3).pin_memory()        # dense, like the IoU term
+    pts_h, nrm_h = pts.pin_memory(), nrm.pin_memory()
+    h_h = torch.full((V,), 5e-5).pin_memory()   # clamp floor of the 6-NN rule at this density (rasterizer.py:326)
+
+    # resident copies for the device-timed `value`
+    pts_d = pts_h.to(dev).requires_grad_(True)
+    nrm_d, col_d = nrm_h.to(dev), colours_h.to(dev).requires_grad_(True)
+    proj_d, view_d, h_d, grad_d = proj_h.to(dev), view_h.to(dev), h_h.to(dev), grad_h.to(dev)
+    grad_sync = torch.zeros(P0, 6, device=dev)     # (d pos, d colour-sum) reduced across ranks when world > 1
+
+    def step_resident():
+        pts_d.grad = None
+        col_d.grad = None
+        out = render_points(pts_d, nrm_d, col_d, proj_d, view_d, h_d, prm)
+        out.image.backward(grad_d)
+        return out
+
+    def allreduce_grads():
+        # the one exchange step of the path: sum of point gradients over all views
+        grad_sync[:, :3] = pts_d.grad
+        grad_sync[:, 3:] = col_d.grad.view(V, P0, 3).sum(0)
+        dist.all_reduce(grad_sync)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-timed region: inputs resident in HBM ----
+    for _ in range(max(a.warmup, 3)):
+        step_resident()
+        if world > 1:
+            allreduce_grads()
+    sync_all()
+    _lib.profile_reset(dev)
+    _lib.profile_enable(True, dev)
+    launches0 = _lib.launch_count(dev)
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        step_resident()
+        if world > 1:
+            allreduce_grads()
+    e1.record()
+    sync_all()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count(dev) - launches0
+    stages = _lib.profile_read(dev)
+    _lib.profile_enable(False, dev)
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * V * P0 * a.steps / (ms_max * 1e-3) / 1e6
+
+    # ---- end to end through the public API with HOST buffers ----
+    e2e = None
+    if not a.no_e2e:
+        img_h = torch.empty(V, S, S, 4).pin_memory()
+        gpts_h = torch.empty(P0, 3).pin_memory()
+
+        def step_e2e():
+            p = pts_h.to(dev, non_blocking=True).requires_grad_(True)
+            n_ = nrm_h.to(dev, non_blocking=True)
+            c = colours_h.to(dev, non_blocking=True).requires_grad_(True)
+            pj, vw = proj_h.to(dev, non_blocking=True), view_h.to(dev, non_blocking=True)
+            hh, gi = h_h.to(dev, non_blocking=True), grad_h.to(dev, non_blocking=True)
+            out = render_points(p, n_, c, pj, vw, hh, prm)
+            out.image.backward(gi)
+            img_h.copy_(out.image, non_blocking=True)
+            gpts_h.copy_(p.grad, non_blocking=True)
+
+        h2d = sum(x.numel() * x.element_size() for x in (pts_h, nrm_h, colours_h, proj_h, view_h, h_h, grad_h))
+        d2h = sum(x.numel() * x.element_size() for x in (img_h, gpts_h))
+        for _ in range(2):
+            step_e2e()
+        sync_all()
+        n_e2e = max(3, a.steps // 2)
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(n_e2e):
+            step_e2e()
+        f1.record()
+        sync_all()
+        t2 = torch.tensor([f0.elapsed_time(f1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * V * P0 * n_e2e / (float(t2.item()) * 1e-3) / 1e6, "unit": "Msplats/s",
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": n_e2e}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel, from the live per-stage CUDA-event times ----
+    peak, peak_src = load_peaks()
+    total_stage_ms = sum(v[0] for v in stages.values()) or 1.0
+    dom = max(stages, key=lambda k: stages[k][0])
+    dom_ms, dom_n = stages[dom]
+    per_launch_views = V
+    alg = {
+        # algorithmic bytes per launch (one launch covers the V views of a step); DESIGN.md "Roofline"
+        "raster_forward": per_launch_views * (36 * P0 + (16 + 4 * K) * S * S),
+        "occ_backward": per_launch_views * (4 * S * S + 20 * P0 + 8 * P0),
+        "preprocess": per_launch_views * (24 * P0 + 36 * P0),
+        "bin_count": per_launch_views * 20 * P0, "bin_scatter": per_launch_views * 24 * P0,
+        "colour_backward": per_launch_views * ((16 + 8 * K) * S * S + 12 * P0),
+        "chain_world": per_launch_views * 20 * P0 + 24 * P0,
+        "search_radius": per_launch_views * 4 * 9 * P0,
+    }.get(dom, 0)
+    dom_avg_ms = dom_ms / max(dom_n, 1)
+    achieved = alg / (dom_avg_ms * 1e-3) / 1e9 if dom_avg_ms > 0 else 0.0
+    step_bytes = V * algorithmic_bytes_per_view(P0, S, K)
+    step_gbs = step_bytes / (ms_max / a.steps * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "kernel_ms_per_launch": dom_avg_ms, "kernel_share_of_step": dom_ms / total_stage_ms,
+                "stage_ms_per_step": {k: v[0] / a.steps for k, v in stages.items() if v[1]},
+                "whole_step": {"algorithmic_bytes": step_bytes, "achieved": step_gbs, "frac": step_gbs / peak,
+                               "formula": BYTES_PER_SPLAT_FMT}}
+
+    cpu = None
+    if not a.no_cpu_baseline and world == 1:
+        try:
+            cpu = cpu_baseline(a.cpu_sample_points, S, K, 1, 1)
+            cpu.pop("seconds", None)
+        except Exception as e:  # pragma: no cover
+            cpu = {"value": None, "unit": "Msplats/s", "cores": 0, "kind": "unavailable", "sample": repr(e)}
+
+    work_mb = (pts_d.numel() + nrm_d.numel() + col_d.numel() + grad_d.numel()) * 4 / 1e6
+    line = {
+        "metric": "Msplats/s fwd+bwd", "value": value, "unit": "Msplats/s", "n_gpus": world, "steps": a.steps,
+        "warmup": max(a.warmup, 3), "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "synthetic sphere %d pts x %d views/GPU, %dx%d, K=%d, fwd+bwd" % (P0, V, S, S, K),
+                   "views_total": V * world, "parallelism": "views sharded %d/GPU + 1 NCCL allreduce of point grads" % V
+                   if world > 1 else "single GPU",
+                   "l2": "per-step inputs %.0f MB + %.0f MB of splat records exceed the 126 MB L2" % (work_mb, V * P0 * 32 / 1e6),
+                   "settings": "configs/dss.yml:14-22 (cutoff 1, merge 0.05, K=5, radii_s 5, clip 0.05, sigma 1)"},
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

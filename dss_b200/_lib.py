@@ -48,6 +48,11 @@ _SIGNATURES = {
     "dss_destroy": (None, [vp]),
     "dss_scratch_bytes": (C.c_size_t, [vp]),
     "dss_launch_count": (C.c_int64, [vp]),
+    "dss_profile_enable": (C.c_int, [vp, C.c_int]),
+    "dss_profile_reset": (C.c_int, [vp]),
+    "dss_profile_num_stages": (C.c_int, []),
+    "dss_profile_stage_name": (C.c_char_p, [C.c_int]),
+    "dss_profile_read": (C.c_int, [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "dss_exclusive_scan_i32": (C.c_int, [vp, vp, vp, C.c_int64, vp]),
     "dss_grid_insert_points_2d": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
     "dss_grid_counting_sort_2d": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
@@ -125,6 +130,25 @@ def ptr(t):
 
 def launch_count(device=None):
     return int(load().dss_launch_count(ctx(device)))
+
+
+def profile_enable(on, device=None):
+    check(load().dss_profile_enable(ctx(device), int(bool(on))), "dss_profile_enable")
+
+
+def profile_reset(device=None):
+    check(load().dss_profile_reset(ctx(device)), "dss_profile_reset")
+
+
+def profile_read(device=None):
+    """{stage name: (total ms, brackets)} since the last reset; synchronises on the recorded events."""
+    lib = load()
+    out = {}
+    for i in range(lib.dss_profile_num_stages()):
+        ms, n = C.c_double(0.0), C.c_int64(0)
+        check(lib.dss_profile_read(ctx(device), i, C.byref(ms), C.byref(n)), "dss_profile_read")
+        out[lib.dss_profile_stage_name(i).decode()] = (ms.value, n.value)
+    return out
 
 
 def scratch_bytes(device=None):

@@ -43,6 +43,7 @@ int visibility_from_idx(dss_ctx *ctx, const int32_t *idx, int64_t num_pixels, in
                         uint8_t *visible, cudaStream_t st) {
     DSS_CUDA_TRY(cudaMemsetAsync(visible, 0, (size_t)(P > 0 ? P : 0), st));
     if (num_pixels == 0 || P == 0) return DSS_OK;
+    StageScope prof(ctx, ST_VISIBILITY, st);
     visibility_kernel<<<nblocks(num_pixels, 256, ctx->sm_count, 16), 256, 0, st>>>(idx, num_pixels, K, P, visible);
     DSS_LAUNCH_CHECK(ctx);
     return DSS_OK;
@@ -173,6 +174,7 @@ int search_radius(dss_ctx *ctx, const float4 *rec, const float *radii, const uin
     unsigned int *hist = nullptr;
     int rc = ctx_get(ctx, BUF_SELECT, (size_t)N * 4 * 256, &hist);
     if (rc) return rc;
+    StageScope prof(ctx, ST_SEARCH_RADIUS, st);
     DSS_CUDA_TRY(cudaMemsetAsync(hist, 0, (size_t)N * 4 * 256 * sizeof(unsigned int), st));
     if (P0 > 0) {
         dim3 grid(nblocks(P0, 256, ctx->sm_count, 4), N);
@@ -292,6 +294,7 @@ int occ_backward(dss_ctx *ctx, const float4 *rec, const uint8_t *visible, const 
                  const int64_t *num_points, int N, int64_t P0, int S, float *grad_xy, cudaStream_t st) {
     if (N <= 0 || P0 <= 0) return DSS_OK;
     dim3 grid(nblocks(P0, OCC_WARPS * 32, ctx->sm_count, 64), N);
+    StageScope prof(ctx, ST_OCC_BWD, st);
     occ_backward_kernel<<<grid, OCC_WARPS * 32, 0, st>>>(rec, visible, rs, grad_occ, pix_stride, pix_offset,
                                                          first_idx, num_points, P0, S,
                                                          reinterpret_cast<float2 *>(grad_xy));
@@ -321,6 +324,7 @@ zbuf_backward_kernel(const int32_t *__restrict__ idx, const float *__restrict__ 
 int zbuf_backward(dss_ctx *ctx, const int32_t *idx, const float *grad_zbuf, int64_t num_pixels, int K,
                   float *z_grad, int z_stride, cudaStream_t st) {
     if (num_pixels == 0) return DSS_OK;
+    StageScope prof(ctx, ST_ZBUF_BWD, st);
     zbuf_backward_kernel<<<nblocks(num_pixels, 256, ctx->sm_count, 16), 256, 0, st>>>(idx, grad_zbuf, num_pixels,
                                                                                       K, z_grad, z_stride);
     DSS_LAUNCH_CHECK(ctx);
@@ -355,6 +359,7 @@ colour_backward_kernel(const int32_t *__restrict__ idx, const float *__restrict_
 int colour_backward(dss_ctx *ctx, const int32_t *idx, const float *weights, const float *grad_image,
                     int64_t num_pixels, int K, float *grad_colours, cudaStream_t st) {
     if (num_pixels == 0) return DSS_OK;
+    StageScope prof(ctx, ST_COLOUR_BWD, st);
     colour_backward_kernel<<<nblocks(num_pixels, 256, ctx->sm_count, 16), 256, 0, st>>>(
         idx, weights, reinterpret_cast<const float4 *>(grad_image), num_pixels, K, grad_colours);
     DSS_LAUNCH_CHECK(ctx);

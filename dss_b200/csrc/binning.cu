@@ -32,6 +32,7 @@ pack_records_kernel(const float *__restrict__ points, const float *__restrict__ 
 int pack_records(dss_ctx *ctx, const float *points, const float *radii, const float *ellipse, int64_t P,
                  float4 *rec, cudaStream_t st) {
     if (P == 0) return DSS_OK;
+    StageScope prof(ctx, ST_PACK, st);
     pack_records_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(points, radii, ellipse, P, rec);
     DSS_LAUNCH_CHECK(ctx);
     return DSS_OK;
@@ -148,6 +149,7 @@ int bin_count_and_scan(dss_ctx *ctx, const float4 *rec, const int64_t *first_idx
     DSS_CUDA_TRY(cudaMemsetAsync(counts, 0, (size_t)(nb + 1) * sizeof(int32_t), st));
     if (P0 > 0) {
         dim3 grid(blocks_for(P0, 256, ctx->sm_count, 8), N);
+        StageScope prof(ctx, ST_BIN_COUNT, st);
         bin_count_kernel<<<grid, 256, 0, st>>>(rec, first_idx, num_points, P0, S, bin, B, counts);
         DSS_LAUNCH_CHECK(ctx);
     }
@@ -162,6 +164,7 @@ int bin_scatter(dss_ctx *ctx, const float4 *rec, const int64_t *first_idx, const
     DSS_CUDA_TRY(cudaMemcpyAsync(cursors, offsets, (size_t)nb * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
     if (P0 > 0) {
         dim3 grid(blocks_for(P0, 256, ctx->sm_count, 8), N);
+        StageScope prof(ctx, ST_BIN_SCATTER, st);
         bin_scatter_kernel<<<grid, 256, 0, st>>>(rec, first_idx, num_points, P0, S, bin, B, cursors, ids);
         DSS_LAUNCH_CHECK(ctx);
     }

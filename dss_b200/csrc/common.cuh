@@ -58,6 +58,17 @@ enum BufId {
 
 }  // namespace dss
 
+namespace dss {
+enum Stage {
+    ST_PACK = 0, ST_PREPROCESS, ST_BIN_COUNT, ST_SCAN, ST_BIN_SCATTER, ST_RASTER_FWD, ST_VISIBILITY,
+    ST_SEARCH_RADIUS, ST_OCC_BWD, ST_COLOUR_BWD, ST_ZBUF_BWD, ST_CHAIN, ST_GRID, NUM_STAGES
+};
+struct ProfPending {
+    cudaEvent_t a, b;
+    int stage;
+};
+}  // namespace dss
+
 struct dss_ctx {
     int device;
     int sm_count;
@@ -65,11 +76,31 @@ struct dss_ctx {
     size_t cap[dss::NUM_BUFS];
     int64_t launches;
     int64_t *h_pinned;  // small pinned host area for read-backs
+    // optional per-stage device timing (CUDA events on the launch stream), see dss_profile_*
+    int profiling;
+    dss::ProfPending *pending;
+    int n_pending, cap_pending;
+    double stage_ms[dss::NUM_STAGES];
+    int64_t stage_calls[dss::NUM_STAGES];
 };
 
 namespace dss {
 
 int ctx_reserve(dss_ctx *ctx, BufId id, size_t bytes, void **out);
+
+// Scoped stage timer: records an event pair around the enclosed launches when profiling is on.
+void prof_begin(dss_ctx *ctx, int stage, cudaStream_t st);
+void prof_end(dss_ctx *ctx, cudaStream_t st);
+struct StageScope {
+    dss_ctx *ctx;
+    cudaStream_t st;
+    StageScope(dss_ctx *c, int stage, cudaStream_t s) : ctx(c), st(s) {
+        if (ctx->profiling) prof_begin(ctx, stage, st);
+    }
+    ~StageScope() {
+        if (ctx->profiling) prof_end(ctx, st);
+    }
+};
 
 template <typename T>
 inline int ctx_get(dss_ctx *ctx, BufId id, size_t count, T **out) {

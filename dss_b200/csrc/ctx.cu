@@ -1,5 +1,6 @@
 // ctx.cu -- context lifetime, error strings, grow-only scratch, single-pass exclusive scan.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -43,6 +44,49 @@ int ctx_reserve(dss_ctx *ctx, BufId id, size_t bytes, void **out) {
     *out = ctx->buf[id];
     return DSS_OK;
 }
+
+void prof_begin(dss_ctx *ctx, int stage, cudaStream_t st) {
+    if (ctx->n_pending == ctx->cap_pending) {
+        const int ncap = ctx->cap_pending ? ctx->cap_pending * 2 : 256;
+        ProfPending *np = (ProfPending *)realloc(ctx->pending, sizeof(ProfPending) * ncap);
+        if (!np) return;
+        for (int i = ctx->cap_pending; i < ncap; ++i) {
+            np[i].a = nullptr;
+            np[i].b = nullptr;
+        }
+        ctx->pending = np;
+        ctx->cap_pending = ncap;
+    }
+    ProfPending &p = ctx->pending[ctx->n_pending];
+    if (!p.a) cudaEventCreate(&p.a);
+    if (!p.b) cudaEventCreate(&p.b);
+    p.stage = stage;
+    cudaEventRecord(p.a, st);
+}
+
+void prof_end(dss_ctx *ctx, cudaStream_t st) {
+    if (ctx->n_pending >= ctx->cap_pending) return;
+    cudaEventRecord(ctx->pending[ctx->n_pending].b, st);
+    ctx->n_pending++;
+}
+
+static void prof_collect(dss_ctx *ctx) {
+    for (int i = 0; i < ctx->n_pending; ++i) {
+        ProfPending &p = ctx->pending[i];
+        float ms = 0.f;
+        if (cudaEventSynchronize(p.b) == cudaSuccess && cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+            ctx->stage_ms[p.stage] += ms;
+            ctx->stage_calls[p.stage] += 1;
+        } else {
+            cudaGetLastError();
+        }
+    }
+    ctx->n_pending = 0;
+}
+
+static const char *k_stage_names[NUM_STAGES] = {
+    "pack_records", "preprocess", "bin_count", "scan", "bin_scatter", "raster_forward", "visibility",
+    "search_radius", "occ_backward", "colour_backward", "zbuf_backward", "chain_world", "grid_2d"};
 
 // ---------------------------------------------------------------------------------------------
 // Exclusive scan, single pass with decoupled look-back.  Replaces external/prefix_sum
@@ -175,6 +219,7 @@ int exclusive_scan_i32(dss_ctx *ctx, const int32_t *in, int32_t *out, int64_t n,
     if (rc) return rc;
     DSS_CUDA_TRY(cudaMemsetAsync(status, 0, ((size_t)tiles + 1) * sizeof(unsigned long long), st));
     unsigned int *ticket = reinterpret_cast<unsigned int *>(status + tiles);
+    StageScope prof(ctx, ST_SCAN, st);
     scan_kernel<<<(unsigned int)tiles, SCAN_THREADS, 0, st>>>(in, out, n, status, ticket);
     DSS_LAUNCH_CHECK(ctx);
     return DSS_OK;
@@ -215,6 +260,11 @@ int dss_create(dss_ctx **out) {
 
 void dss_destroy(dss_ctx *ctx) {
     if (!ctx) return;
+    for (int i = 0; i < ctx->cap_pending; ++i) {
+        if (ctx->pending[i].a) cudaEventDestroy(ctx->pending[i].a);
+        if (ctx->pending[i].b) cudaEventDestroy(ctx->pending[i].b);
+    }
+    free(ctx->pending);
     for (int i = 0; i < dss::NUM_BUFS; ++i)
         if (ctx->buf[i]) cudaFree(ctx->buf[i]);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
@@ -229,6 +279,38 @@ size_t dss_scratch_bytes(const dss_ctx *ctx) {
 }
 
 int64_t dss_launch_count(const dss_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int dss_profile_enable(dss_ctx *ctx, int on) {
+    DSS_REQUIRE(ctx != nullptr, "ctx is null");
+    if (!on && ctx->profiling) dss::prof_collect(ctx);
+    ctx->profiling = on ? 1 : 0;
+    return DSS_OK;
+}
+
+int dss_profile_reset(dss_ctx *ctx) {
+    DSS_REQUIRE(ctx != nullptr, "ctx is null");
+    dss::prof_collect(ctx);
+    for (int i = 0; i < dss::NUM_STAGES; ++i) {
+        ctx->stage_ms[i] = 0.0;
+        ctx->stage_calls[i] = 0;
+    }
+    return DSS_OK;
+}
+
+int dss_profile_num_stages(void) { return dss::NUM_STAGES; }
+
+const char *dss_profile_stage_name(int stage) {
+    return (stage >= 0 && stage < dss::NUM_STAGES) ? dss::k_stage_names[stage] : "";
+}
+
+int dss_profile_read(dss_ctx *ctx, int stage, double *total_ms, int64_t *brackets) {
+    DSS_REQUIRE(ctx != nullptr, "ctx is null");
+    DSS_REQUIRE(stage >= 0 && stage < dss::NUM_STAGES, "stage out of range");
+    dss::prof_collect(ctx);
+    if (total_ms) *total_ms = ctx->stage_ms[stage];
+    if (brackets) *brackets = ctx->stage_calls[stage];
+    return DSS_OK;
+}
 
 int dss_exclusive_scan_i32(dss_ctx *ctx, const int32_t *in, int32_t *out, int64_t n, void *stream) {
     DSS_REQUIRE(ctx != nullptr, "ctx is null");

@@ -184,6 +184,7 @@ raster_fwd_kernel(const __grid_constant__ RasterArgs a) {
 template <int KMAX>
 static int launch_raster(dss_ctx *ctx, const RasterArgs &a, cudaStream_t st) {
     dim3 grid((unsigned)(a.B * a.B), (unsigned)a.N);
+    StageScope prof(ctx, ST_RASTER_FWD, st);
     const bool blend = a.image != nullptr;
     if (blend) {
         if (a.cutoff)

@@ -153,6 +153,7 @@ static int run_preprocess(dss_ctx *ctx, const dss_render_args *g, float4 *rec, c
     a.radii = g->radii;
     a.scaler = g->scaler;
     dim3 grid(nblocks(g->P0, 256, ctx->sm_count, 8), g->n_views);
+    StageScope prof(ctx, ST_PREPROCESS, st);
     preprocess_kernel<<<grid, 256, 0, st>>>(a);
     DSS_LAUNCH_CHECK(ctx);
     return DSS_OK;
@@ -368,6 +369,7 @@ int dss_render_backward(dss_ctx *ctx, const dss_render_args *g, void *stream) {
     c.clip = g->clip_pts_grad;
     c.grad_ndc = g->grad_ndc;
     c.grad_world = g->grad_points_world;
+    StageScope prof(ctx, ST_CHAIN, st);
     if (g->shared_cloud) {
         DSS_REQUIRE(N <= 256, "shared-cloud backward supports at most 256 views per call");
         chain_kernel<<<nblocks(g->P0, 256, ctx->sm_count, 8), 256, (size_t)N * 32 * sizeof(float), st>>>(c);

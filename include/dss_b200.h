@@ -54,6 +54,17 @@ DSS_API size_t dss_scratch_bytes(const dss_ctx *ctx);/* device bytes currently h
 /* number of kernels the library has launched on this context since creation (bench: gpu_launches) */
 DSS_API int64_t dss_launch_count(const dss_ctx *ctx);
 
+/* ---- optional per-stage device timing ------------------------------------------------------
+ * When enabled, every stage (preprocess, bin count, scan, scatter, raster, ...) is bracketed by a CUDA
+ * event pair on the launch stream.  dss_profile_read synchronises on the recorded events and returns
+ * the accumulated milliseconds and number of brackets of one stage since the last reset.  Used by
+ * bench.py for the live roofline of the dominant kernel; off by default (zero overhead). */
+DSS_API int dss_profile_enable(dss_ctx *ctx, int on);
+DSS_API int dss_profile_reset(dss_ctx *ctx);
+DSS_API int dss_profile_num_stages(void);
+DSS_API const char *dss_profile_stage_name(int stage);
+DSS_API int dss_profile_read(dss_ctx *ctx, int stage, double *total_ms, int64_t *brackets);
+
 /* ---- exclusive prefix sum -----------------------------------------------------------------
  * Replaces prefix_sum.prefix_sum_cuda(grid_cnt, num_grids, grid_off)
  * (external/prefix_sum/prefix_sum.h:6-21, prefix_sum.cu:74-87,135-205): exclusive int32 scan of the
