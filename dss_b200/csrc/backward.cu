@@ -195,17 +195,185 @@ int search_radius(dss_ctx *ctx, const float4 *rec, const float *radii, const uin
 // ones are processed in turn; each lane finally stores the result of "its" splat (coalesced float2).
 // ---------------------------------------------------------------------------------------------
 constexpr int OCC_WARPS = 8;
+constexpr int OCC_TILE = 32;          // pixels per side of a backward tile
+constexpr int OCC_TILE_THREADS = 256;
+
+// Does the (tile + 2R)^2 window of alpha gradients fit the tile kernel's shared memory?  Evaluated
+// identically on the device by both kernels so that every view is processed by exactly one of them.
+__host__ __device__ __forceinline__ int occ_halo(float r, int S) { return (int)ceilf(r * 0.5f * (float)S) + 2; }
+__host__ __device__ __forceinline__ bool occ_tile_fits(float r, int S, int smem_bytes) {
+    if (!(r >= 0.0f) || !(r < 4.0f) || smem_bytes <= 0) return false;
+    const int side = OCC_TILE + 2 * occ_halo(r, S);
+    return (size_t)side * side * sizeof(float) <= (size_t)smem_bytes;
+}
+
+__device__ __forceinline__ int centre_tile(float px, float py, int S, int OB) {
+    const float half_S = 0.5f * (float)S;
+    const int xi = min(max((int)floorf((px + 1.0f) * half_S), 0), S - 1);
+    const int yi = min(max((int)floorf((py + 1.0f) * half_S), 0), S - 1);
+    return (yi / OCC_TILE) * OB + (xi / OCC_TILE);
+}
+
+__device__ __forceinline__ bool occ_eligible(const float4 A) {
+    // rasterize_points_backward.cu:145 -- outside the renderable area
+    return !(A.z < 0.0f || fabsf(A.y) > 1.0f || fabsf(A.x) > 1.0f);
+}
+
+// Bin the visible, eligible splats by the 32x32 tile that contains their centre (one tile per splat,
+// so the id list is bounded by P and no host round-trip is needed).  PASS 0 counts, PASS 1 scatters.
+template <int PASS>
+__global__ void __launch_bounds__(256)
+occ_bin_kernel(const float4 *__restrict__ rec, const uint8_t *__restrict__ visible,
+               const int64_t *__restrict__ first_idx, const int64_t *__restrict__ num_points,
+               int64_t P0_shared, int S, int OB, int32_t *__restrict__ counters, int32_t *__restrict__ ids) {
+    extern __shared__ int32_t s_hist[];
+    const int n = blockIdx.y;
+    const int nt = OB * OB;
+    const ViewRange vr = view_range(first_idx, num_points, n, P0_shared);
+    constexpr int ITEMS = 8;
+    const int64_t chunk0 = (int64_t)blockIdx.x * (256 * ITEMS);
+    if (chunk0 >= vr.count) return;
+    for (int t = threadIdx.x; t < nt; t += 256) s_hist[t] = 0;
+    __syncthreads();
+    int tile[ITEMS];
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+        tile[j] = -1;
+        const int64_t i = chunk0 + j * 256 + threadIdx.x;
+        if (i < vr.count && visible[vr.first + i]) {
+            const float4 A = __ldg(&rec[2 * (vr.first + i)]);
+            if (occ_eligible(A)) {
+                tile[j] = centre_tile(A.x, A.y, S, OB);
+                atomicAdd(&s_hist[tile[j]], 1);
+            }
+        }
+    }
+    __syncthreads();
+    int32_t *cnt = counters + (int64_t)n * nt;
+    for (int t = threadIdx.x; t < nt; t += 256) {
+        const int v = s_hist[t];
+        if (v) {
+            const int base = atomicAdd(&cnt[t], v);
+            if (PASS == 1) s_hist[t] = base;
+        }
+    }
+    if (PASS == 0) return;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j)
+        if (tile[j] >= 0) ids[atomicAdd(&s_hist[tile[j]], 1)] = (int32_t)(vr.first + chunk0 + j * 256 + threadIdx.x);
+}
+
+// One CTA per (32x32 tile, view): the tile's window of alpha gradients (tile + halo of the search radius)
+// is staged in shared memory once; each warp then takes splats of the tile's list and gathers over the
+// splat's own (2R+1)^2 sub-window with conflict-free shared-memory reads.
+__global__ void __launch_bounds__(OCC_TILE_THREADS)
+occ_tile_kernel(const float4 *__restrict__ rec, const float *__restrict__ rs, const float *__restrict__ grad,
+                int pix_stride, int pix_offset, const int32_t *__restrict__ tile_offsets,
+                const int32_t *__restrict__ tile_ids, int S, int OB, int smem_bytes, float2 *__restrict__ grad_xy) {
+    extern __shared__ float s_g[];
+    const int n = blockIdx.y, tile = blockIdx.x;
+    const float r = rs[n];
+    if (!occ_tile_fits(r, S, smem_bytes)) return;
+    const int64_t tb = (int64_t)n * OB * OB + tile;
+    const int beg = tile_offsets[tb], end = tile_offsets[tb + 1];
+    if (beg == end) return;
+    const int R = occ_halo(r, S);
+    const int side = OCC_TILE + 2 * R;
+    const int ty = tile / OB, tx = tile - ty * OB;
+    const int wx0 = tx * OCC_TILE - R, wy0 = ty * OCC_TILE - R;
+    const float *gview = grad + ((int64_t)n * S * S) * pix_stride + pix_offset;
+    for (int i = threadIdx.x; i < side * side; i += OCC_TILE_THREADS) {
+        const int wy = i / side, wx = i - wy * side;
+        const int xi = wx0 + wx, yi = wy0 + wy;
+        float g = 0.0f;
+        if (xi >= 0 && xi < S && yi >= 0 && yi < S)
+            g = __ldg(gview + ((int64_t)(S - 1 - yi) * S + (S - 1 - xi)) * pix_stride);
+        s_g[i] = g;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float r2 = r * r;
+    const bool pow2 = (S & (S - 1)) == 0;
+    const float inv_S = 1.0f / (float)S, half_S = 0.5f * (float)S;
+    constexpr unsigned FULL = 0xffffffffu;
+    // Lane <-> window column, loop over window rows.  dx (hence dx^2 and the x half of the bbox test) is
+    // a per-lane constant of the splat, dy is shared by the row, and since dx is constant along a column
+    //     sum_rows dx * w = dx * sum_rows w ,   w = g / max(d2, 1e-10)
+    // each pair costs one reciprocal, one add and one fma.  Narrow windows pack several splats per warp.
+    const int Rw = R - 1;                       // per-splat window half-width in pixels (covers the disc)
+    const int Wwin = 2 * Rw + 1;
+    const int lpp = Wwin <= 8 ? 8 : (Wwin <= 16 ? 16 : 32);   // lanes per splat
+    const int groups = 32 / lpp;
+    const int grp = lane / lpp, gl = lane - grp * lpp;
+    const int nwarps = OCC_TILE_THREADS / 32;
+    for (int k0 = beg + warp * groups; k0 < end; k0 += nwarps * groups) {
+        const int k = k0 + grp;
+        const bool have = k < end;
+        const int p = have ? tile_ids[k] : 0;
+        float px = 0.f, py = 0.f, rx = 0.f, ry = 0.f;
+        if (have) {
+            const float4 A = __ldg(&rec[2 * (int64_t)p]);
+            px = A.x;
+            py = A.y;
+            rx = A.w;
+            ry = __ldg(&rec[2 * (int64_t)p + 1]).x;
+        }
+        const int cx = min(max((int)floorf((px + 1.0f) * half_S), 0), S - 1);
+        const int cy = min(max((int)floorf((py + 1.0f) * half_S), 0), S - 1);
+        float gx = 0.f, gy = 0.f;
+        for (int cb = 0; cb < Wwin; cb += lpp) {            // column blocks (one unless the window is > 32 wide)
+            const int xi = cx - Rw + cb + gl;
+            const bool col_ok = have && (cb + gl < Wwin) && xi >= 0 && xi < S;
+            const float dx = pix_to_ndc_fast(xi, S, inv_S, pow2) - px;
+            const float dx2 = dx * dx;
+            const bool out_x = fabsf(dx) > rx;
+            const float *col = s_g + (xi - wx0);
+            float sw = 0.f, swy = 0.f;
+            for (int j = 0; j < Wwin; ++j) {
+                const int yi = cy - Rw + j;
+                if (col_ok && yi >= 0 && yi < S) {
+                    const float g = col[(yi - wy0) * side];
+                    const float dy = pix_to_ndc_fast(yi, S, inv_S, pow2) - py;
+                    const float d2 = fmaf(dy, dy, dx2);
+                    const bool outside = out_x || (fabsf(dy) > ry);
+                    // rasterize_points_backward.cu:156-172
+                    if (g != 0.0f && !(d2 > r2) && !(g > 0.0f && outside)) {
+                        const float w = g * __frcp_rn(fmaxf(d2, 1e-10f));
+                        sw += w;
+                        swy = fmaf(w, dy, swy);
+                    }
+                }
+            }
+            gx = fmaf(dx, sw, gx);
+            gy += swy;
+        }
+        for (int d = lpp >> 1; d > 0; d >>= 1) {
+            gx += __shfl_xor_sync(FULL, gx, d);
+            gy += __shfl_xor_sync(FULL, gy, d);
+        }
+        if (have && gl == 0) grad_xy[p] = make_float2(gx, gy);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Occupancy gather.  One warp per visible splat; lanes stride over the (2R+1)^2 pixel window that
+// conservatively contains the disc of radius r_n, evaluate the reference's per-pair rule
+// (rasterize_points_backward.cu:141-178) and warp-reduce.  32 consecutive splats per warp, the visible
+// ones are processed in turn; each lane finally stores the result of "its" splat (coalesced float2).
+// ---------------------------------------------------------------------------------------------
 
 __global__ void __launch_bounds__(OCC_WARPS * 32)
 occ_backward_kernel(const float4 *__restrict__ rec, const uint8_t *__restrict__ visible,
                     const float *__restrict__ rs, const float *__restrict__ grad, int pix_stride,
                     int pix_offset, const int64_t *__restrict__ first_idx,
-                    const int64_t *__restrict__ num_points, int64_t P0_shared, int S,
+                    const int64_t *__restrict__ num_points, int64_t P0_shared, int S, int fast_smem_bytes,
                     float2 *__restrict__ grad_xy) {
     const int n = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const ViewRange vr = view_range(first_idx, num_points, n, P0_shared);
     const float r = rs[n];
+    if (occ_tile_fits(r, S, fast_smem_bytes)) return;   // this view is handled by occ_tile_kernel
     const float r2 = r * r;
     const bool pow2 = (S & (S - 1)) == 0;
     const float inv_S = 1.0f / (float)S;
@@ -293,12 +461,59 @@ int occ_backward(dss_ctx *ctx, const float4 *rec, const uint8_t *visible, const 
                  const float *grad_occ, int pix_stride, int pix_offset, const int64_t *first_idx,
                  const int64_t *num_points, int N, int64_t P0, int S, float *grad_xy, cudaStream_t st) {
     if (N <= 0 || P0 <= 0) return DSS_OK;
-    dim3 grid(nblocks(P0, OCC_WARPS * 32, ctx->sm_count, 64), N);
+    const int OB = (S + OCC_TILE - 1) / OCC_TILE;
+    const int64_t nt = (int64_t)N * OB * OB;
+    // shared-memory budget of the tile kernel from the radii seen by the previous call (a hint only:
+    // both kernels re-derive "fits" from the current radius on the device)
+    float hint = 0.0f;
+    float *h_rs = reinterpret_cast<float *>(ctx->h_pinned + 8);
+    for (int i = 0; i < (N < 96 ? N : 96); ++i) hint = fmaxf(hint, h_rs[i]);
+    int smem = 64 * 1024;
+    if (hint > 0.0f && hint < 4.0f) {
+        const int side = OCC_TILE + 2 * (occ_halo(hint * 1.25f, S) + 1);
+        smem = side * side * (int)sizeof(float);
+        if (smem < 16 * 1024) smem = 16 * 1024;
+        if (smem > 200 * 1024) smem = 200 * 1024;
+    }
+    const bool tiles_ok = (size_t)OB * OB * sizeof(int32_t) <= 200 * 1024 && nt + 1 < (int64_t)INT32_MAX;
+    if (!tiles_ok) smem = 0;
+    int rc;
     StageScope prof(ctx, ST_OCC_BWD, st);
+    if (smem > 0) {
+        int32_t *counts = nullptr, *offsets = nullptr, *ids = nullptr;
+        if ((rc = ctx_get(ctx, BUF_TILE_COUNTS, (size_t)(nt + 1), &counts))) return rc;
+        if ((rc = ctx_get(ctx, BUF_TILE_OFFSETS, (size_t)(nt + 1), &offsets))) return rc;
+        const int64_t Ptot = (first_idx == nullptr) ? (int64_t)N * P0 : P0;   // packed mode passes P0 = P
+        if ((rc = ctx_get(ctx, BUF_TILE_IDS, (size_t)(Ptot > 0 ? Ptot : 1), &ids))) return rc;
+        DSS_CUDA_TRY(cudaMemsetAsync(counts, 0, (size_t)(nt + 1) * sizeof(int32_t), st));
+        dim3 bgrid((unsigned)((P0 + 2047) / 2048), N);
+        const size_t hist = (size_t)OB * OB * sizeof(int32_t);
+        if (hist > 48 * 1024) {
+            DSS_CUDA_TRY(cudaFuncSetAttribute(occ_bin_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist));
+            DSS_CUDA_TRY(cudaFuncSetAttribute(occ_bin_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist));
+        }
+        occ_bin_kernel<0><<<bgrid, 256, hist, st>>>(rec, visible, first_idx, num_points, P0, S, OB, counts, nullptr);
+        DSS_LAUNCH_CHECK(ctx);
+        if ((rc = exclusive_scan_i32(ctx, counts, offsets, nt + 1, st))) return rc;
+        DSS_CUDA_TRY(cudaMemcpyAsync(counts, offsets, (size_t)nt * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+        occ_bin_kernel<1><<<bgrid, 256, hist, st>>>(rec, visible, first_idx, num_points, P0, S, OB, counts, ids);
+        DSS_LAUNCH_CHECK(ctx);
+        DSS_CUDA_TRY(cudaMemsetAsync(grad_xy, 0, (size_t)Ptot * 2 * sizeof(float), st));
+        if (smem > 48 * 1024)
+            DSS_CUDA_TRY(cudaFuncSetAttribute(occ_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        dim3 tgrid((unsigned)(OB * OB), N);
+        occ_tile_kernel<<<tgrid, OCC_TILE_THREADS, smem, st>>>(rec, rs, grad_occ, pix_stride, pix_offset, offsets, ids,
+                                                              S, OB, smem, reinterpret_cast<float2 *>(grad_xy));
+        DSS_LAUNCH_CHECK(ctx);
+    }
+    // views whose window does not fit (very large search radius) take the direct global-memory gather
+    dim3 grid(nblocks(P0, OCC_WARPS * 32, ctx->sm_count, 64), N);
     occ_backward_kernel<<<grid, OCC_WARPS * 32, 0, st>>>(rec, visible, rs, grad_occ, pix_stride, pix_offset,
-                                                         first_idx, num_points, P0, S,
+                                                         first_idx, num_points, P0, S, smem,
                                                          reinterpret_cast<float2 *>(grad_xy));
     DSS_LAUNCH_CHECK(ctx);
+    // refresh the hint for the next call (asynchronous; may be read stale, it is only a hint)
+    DSS_CUDA_TRY(cudaMemcpyAsync(h_rs, rs, (size_t)(N < 96 ? N : 96) * sizeof(float), cudaMemcpyDeviceToHost, st));
     return DSS_OK;
 }
 

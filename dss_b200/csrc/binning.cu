@@ -90,45 +90,117 @@ __device__ __forceinline__ BinRect splat_bin_rect(const float4 A, const float ry
     return r;
 }
 
-// grid: (blocks, N).  counts: (N*B*B) zero-initialised.
-__global__ void __launch_bounds__(256)
+// ---------------------------------------------------------------------------------------------
+// count / scatter with block-level aggregation.  A block owns a contiguous chunk of BIN_ITEMS*256
+// splats of one view, keeps the per-tile histogram of that chunk in shared memory and touches global
+// memory with ONE atomic per (block, non-empty tile) instead of one per (splat, tile): the per-tile
+// counters are a few hundred hot addresses and L2 serialises same-address atomics.
+// Fallback (plain global atomics) when the histogram of B*B tiles does not fit in shared memory.
+// ---------------------------------------------------------------------------------------------
+constexpr int BIN_THREADS = 256;
+constexpr int BIN_ITEMS = 8;
+constexpr int BIN_CHUNK = BIN_THREADS * BIN_ITEMS;
+constexpr int BIN_MAX_SMEM_TILES = 48 * 1024;   // 192 KB of histogram at most
+
+__device__ __forceinline__ int2 pack_rect(const BinRect &r) {
+    return r.empty ? make_int2(-1, -1) : make_int2(r.x0 | (r.x1 << 16), r.y0 | (r.y1 << 16));
+}
+
+template <bool SMEM>
+__global__ void __launch_bounds__(BIN_THREADS)
 bin_count_kernel(const float4 *__restrict__ rec, const int64_t *__restrict__ first_idx,
                  const int64_t *__restrict__ num_points, int64_t P0_shared, int S, int bin, int B,
                  int32_t *__restrict__ counts) {
+    extern __shared__ int32_t s_hist[];
     const int n = blockIdx.y;
+    const int nt = B * B;
     const ViewRange vr = view_range(first_idx, num_points, n, P0_shared);
-    int32_t *cnt = counts + (int64_t)n * B * B;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < vr.count;
-         i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t chunk0 = (int64_t)blockIdx.x * BIN_CHUNK;
+    if (chunk0 >= vr.count) return;
+    int32_t *cnt = counts + (int64_t)n * nt;
+    if (SMEM) {
+        for (int t = threadIdx.x; t < nt; t += BIN_THREADS) s_hist[t] = 0;
+        __syncthreads();
+    }
+#pragma unroll 2
+    for (int j = 0; j < BIN_ITEMS; ++j) {
+        const int64_t i = chunk0 + j * BIN_THREADS + threadIdx.x;
+        if (i >= vr.count) break;
         const int64_t p = vr.first + i;
         const float4 A = __ldg(&rec[2 * p]);
         const float ry = __ldg(&rec[2 * p + 1]).x;
         const BinRect r = splat_bin_rect(A, ry, bin, S, B);
         if (r.empty) continue;
         for (int by = r.y0; by <= r.y1; ++by)
-            for (int bx = r.x0; bx <= r.x1; ++bx) atomicAdd(&cnt[by * B + bx], 1);
+            for (int bx = r.x0; bx <= r.x1; ++bx) atomicAdd(SMEM ? &s_hist[by * B + bx] : &cnt[by * B + bx], 1);
+    }
+    if (SMEM) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < nt; t += BIN_THREADS) {
+            const int v = s_hist[t];
+            if (v) atomicAdd(&cnt[t], v);
+        }
     }
 }
 
 // cursors: copy of offsets (N*B*B), advanced atomically; ids: CSR payload.
-__global__ void __launch_bounds__(256)
+template <bool SMEM>
+__global__ void __launch_bounds__(BIN_THREADS)
 bin_scatter_kernel(const float4 *__restrict__ rec, const int64_t *__restrict__ first_idx,
                    const int64_t *__restrict__ num_points, int64_t P0_shared, int S, int bin, int B,
                    int32_t *__restrict__ cursors, int32_t *__restrict__ ids) {
+    extern __shared__ int32_t s_hist[];
     const int n = blockIdx.y;
+    const int nt = B * B;
     const ViewRange vr = view_range(first_idx, num_points, n, P0_shared);
-    int32_t *cur = cursors + (int64_t)n * B * B;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < vr.count;
-         i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t p = vr.first + i;
-        const float4 A = __ldg(&rec[2 * p]);
-        const float ry = __ldg(&rec[2 * p + 1]).x;
-        const BinRect r = splat_bin_rect(A, ry, bin, S, B);
-        if (r.empty) continue;
-        for (int by = r.y0; by <= r.y1; ++by)
-            for (int bx = r.x0; bx <= r.x1; ++bx) {
-                const int slot = atomicAdd(&cur[by * B + bx], 1);
-                ids[slot] = (int32_t)p;
+    const int64_t chunk0 = (int64_t)blockIdx.x * BIN_CHUNK;
+    if (chunk0 >= vr.count) return;
+    int32_t *cur = cursors + (int64_t)n * nt;
+    if (SMEM) {
+        for (int t = threadIdx.x; t < nt; t += BIN_THREADS) s_hist[t] = 0;
+        __syncthreads();
+    }
+    int2 rect[BIN_ITEMS];
+#pragma unroll
+    for (int j = 0; j < BIN_ITEMS; ++j) {
+        rect[j] = make_int2(-1, -1);
+        const int64_t i = chunk0 + j * BIN_THREADS + threadIdx.x;
+        if (i < vr.count) {
+            const int64_t p = vr.first + i;
+            const float4 A = __ldg(&rec[2 * p]);
+            const float ry = __ldg(&rec[2 * p + 1]).x;
+            const BinRect r = splat_bin_rect(A, ry, bin, S, B);
+            rect[j] = pack_rect(r);
+            if (!r.empty) {
+                for (int by = r.y0; by <= r.y1; ++by)
+                    for (int bx = r.x0; bx <= r.x1; ++bx) {
+                        if (SMEM) {
+                            atomicAdd(&s_hist[by * B + bx], 1);
+                        } else {
+                            const int slot = atomicAdd(&cur[by * B + bx], 1);
+                            ids[slot] = (int32_t)p;
+                        }
+                    }
+            }
+        }
+    }
+    if (!SMEM) return;
+    __syncthreads();
+    // reserve a contiguous range per non-empty tile; s_hist becomes the block's write cursor
+    for (int t = threadIdx.x; t < nt; t += BIN_THREADS) {
+        const int v = s_hist[t];
+        if (v) s_hist[t] = atomicAdd(&cur[t], v);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < BIN_ITEMS; ++j) {
+        if (rect[j].x < 0) continue;
+        const int x0 = rect[j].x & 0xffff, x1 = rect[j].x >> 16, y0 = rect[j].y & 0xffff, y1 = rect[j].y >> 16;
+        const int32_t p = (int32_t)(vr.first + chunk0 + j * BIN_THREADS + threadIdx.x);
+        for (int by = y0; by <= y1; ++by)
+            for (int bx = x0; bx <= x1; ++bx) {
+                const int slot = atomicAdd(&s_hist[by * B + bx], 1);
+                ids[slot] = p;
             }
     }
 }
@@ -141,6 +213,13 @@ static inline unsigned int blocks_for(int64_t work_items, int threads, int sm_co
     return (unsigned int)b;
 }
 
+template <typename Kern>
+static int prepare_smem(Kern kern, size_t bytes) {
+    if (bytes > 48 * 1024)
+        DSS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return DSS_OK;
+}
+
 // count + scan.  offsets must have N*B*B + 1 entries; counts N*B*B + 1 (last stays 0).
 int bin_count_and_scan(dss_ctx *ctx, const float4 *rec, const int64_t *first_idx, const int64_t *num_points,
                        int N, int64_t P0, int S, int bin, int32_t *counts, int32_t *offsets, cudaStream_t st) {
@@ -148,9 +227,16 @@ int bin_count_and_scan(dss_ctx *ctx, const float4 *rec, const int64_t *first_idx
     const int64_t nb = (int64_t)N * B * B;
     DSS_CUDA_TRY(cudaMemsetAsync(counts, 0, (size_t)(nb + 1) * sizeof(int32_t), st));
     if (P0 > 0) {
-        dim3 grid(blocks_for(P0, 256, ctx->sm_count, 8), N);
+        dim3 grid((unsigned)((P0 + BIN_CHUNK - 1) / BIN_CHUNK), N);
         StageScope prof(ctx, ST_BIN_COUNT, st);
-        bin_count_kernel<<<grid, 256, 0, st>>>(rec, first_idx, num_points, P0, S, bin, B, counts);
+        if (B * B <= BIN_MAX_SMEM_TILES && B < 32768) {
+            const size_t smem = (size_t)B * B * sizeof(int32_t);
+            int rc = prepare_smem(bin_count_kernel<true>, smem);
+            if (rc) return rc;
+            bin_count_kernel<true><<<grid, BIN_THREADS, smem, st>>>(rec, first_idx, num_points, P0, S, bin, B, counts);
+        } else {
+            bin_count_kernel<false><<<grid, BIN_THREADS, 0, st>>>(rec, first_idx, num_points, P0, S, bin, B, counts);
+        }
         DSS_LAUNCH_CHECK(ctx);
     }
     return exclusive_scan_i32(ctx, counts, offsets, nb + 1, st);
@@ -163,9 +249,16 @@ int bin_scatter(dss_ctx *ctx, const float4 *rec, const int64_t *first_idx, const
     const int64_t nb = (int64_t)N * B * B;
     DSS_CUDA_TRY(cudaMemcpyAsync(cursors, offsets, (size_t)nb * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
     if (P0 > 0) {
-        dim3 grid(blocks_for(P0, 256, ctx->sm_count, 8), N);
+        dim3 grid((unsigned)((P0 + BIN_CHUNK - 1) / BIN_CHUNK), N);
         StageScope prof(ctx, ST_BIN_SCATTER, st);
-        bin_scatter_kernel<<<grid, 256, 0, st>>>(rec, first_idx, num_points, P0, S, bin, B, cursors, ids);
+        if (B * B <= BIN_MAX_SMEM_TILES && B < 32768) {
+            const size_t smem = (size_t)B * B * sizeof(int32_t);
+            int rc = prepare_smem(bin_scatter_kernel<true>, smem);
+            if (rc) return rc;
+            bin_scatter_kernel<true><<<grid, BIN_THREADS, smem, st>>>(rec, first_idx, num_points, P0, S, bin, B, cursors, ids);
+        } else {
+            bin_scatter_kernel<false><<<grid, BIN_THREADS, 0, st>>>(rec, first_idx, num_points, P0, S, bin, B, cursors, ids);
+        }
         DSS_LAUNCH_CHECK(ctx);
     }
     return DSS_OK;

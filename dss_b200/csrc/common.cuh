@@ -66,6 +66,7 @@ enum Stage {
 struct ProfPending {
     cudaEvent_t a, b;
     int stage;
+    int closed;
 };
 }  // namespace dss
 
@@ -80,6 +81,7 @@ struct dss_ctx {
     int profiling;
     dss::ProfPending *pending;
     int n_pending, cap_pending;
+    int open[8], n_open;
     double stage_ms[dss::NUM_STAGES];
     int64_t stage_calls[dss::NUM_STAGES];
 };

@@ -46,10 +46,18 @@ int ctx_reserve(dss_ctx *ctx, BufId id, size_t bytes, void **out) {
 }
 
 void prof_begin(dss_ctx *ctx, int stage, cudaStream_t st) {
+    // scopes may nest (e.g. the scan inside the occupancy backward): keep a small stack of open entries
+    if (ctx->n_open >= 8) {
+        ctx->open[ctx->n_open++ & 7] = -1;
+        return;
+    }
     if (ctx->n_pending == ctx->cap_pending) {
         const int ncap = ctx->cap_pending ? ctx->cap_pending * 2 : 256;
         ProfPending *np = (ProfPending *)realloc(ctx->pending, sizeof(ProfPending) * ncap);
-        if (!np) return;
+        if (!np) {
+            ctx->open[ctx->n_open++] = -1;
+            return;
+        }
         for (int i = ctx->cap_pending; i < ncap; ++i) {
             np[i].a = nullptr;
             np[i].b = nullptr;
@@ -57,23 +65,29 @@ void prof_begin(dss_ctx *ctx, int stage, cudaStream_t st) {
         ctx->pending = np;
         ctx->cap_pending = ncap;
     }
-    ProfPending &p = ctx->pending[ctx->n_pending];
+    const int slot = ctx->n_pending++;
+    ProfPending &p = ctx->pending[slot];
     if (!p.a) cudaEventCreate(&p.a);
     if (!p.b) cudaEventCreate(&p.b);
     p.stage = stage;
+    p.closed = 0;
     cudaEventRecord(p.a, st);
+    ctx->open[ctx->n_open++] = slot;
 }
 
 void prof_end(dss_ctx *ctx, cudaStream_t st) {
-    if (ctx->n_pending >= ctx->cap_pending) return;
-    cudaEventRecord(ctx->pending[ctx->n_pending].b, st);
-    ctx->n_pending++;
+    if (ctx->n_open <= 0) return;
+    const int slot = ctx->open[--ctx->n_open & 7];
+    if (slot < 0) return;
+    cudaEventRecord(ctx->pending[slot].b, st);
+    ctx->pending[slot].closed = 1;
 }
 
 static void prof_collect(dss_ctx *ctx) {
     for (int i = 0; i < ctx->n_pending; ++i) {
         ProfPending &p = ctx->pending[i];
         float ms = 0.f;
+        if (!p.closed) continue;
         if (cudaEventSynchronize(p.b) == cudaSuccess && cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
             ctx->stage_ms[p.stage] += ms;
             ctx->stage_calls[p.stage] += 1;
@@ -82,6 +96,7 @@ static void prof_collect(dss_ctx *ctx) {
         }
     }
     ctx->n_pending = 0;
+    ctx->n_open = 0;
 }
 
 static const char *k_stage_names[NUM_STAGES] = {
@@ -254,6 +269,7 @@ int dss_create(dss_ctx **out) {
         dss::set_error("pinned host allocation failed");
         return DSS_E_NOMEM;
     }
+    memset(c->h_pinned, 0, 64 * sizeof(int64_t));
     *out = c;
     return DSS_OK;
 }

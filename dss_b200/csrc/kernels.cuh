@@ -37,6 +37,7 @@ struct RasterArgs {
     float *image;          // (N,S,S,4)
     float *weights;        // (N,S,S,K)
     uint8_t *visible;      // (P,) must be zeroed by the caller
+    int force_pixel_parallel;  // testing: use the pixel-parallel kernel even for K <= 8
 };
 
 int raster_forward(dss_ctx *ctx, const RasterArgs &a, cudaStream_t st);

@@ -181,6 +181,185 @@ raster_fwd_kernel(const __grid_constant__ RasterArgs a) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Splat-parallel ("scatter") rasterizer, the production path for K <= 8.
+//
+// The pixel-parallel kernel above tests every splat that overlaps a warp's 8x4 patch in all 32 lanes,
+// although a ~5 px splat covers only ~1/5 of them.  Here the roles are swapped: the per-pixel K-nearest
+// lists of a 16x16 tile live in SHARED memory as sorted 64-bit keys (z bits << 32 | id), every THREAD
+// takes its own splat of the tile list and walks only the pixels of that splat's bounding box inside
+// the tile:  key >= pixel's current K-th key -> skip (one LDS.64 + compare);  otherwise the reference's
+// exact test (rasterize_points.cu:87-97) and a lock-free sorted insert: a chain of atomicMin on the K
+// slots, each step keeping the smaller key and carrying the larger one to the next slot.  The slots end
+// up holding the K smallest keys in ascending (z, id) order whatever the interleaving, so the result is
+// deterministic and identical to the pixel-parallel kernel.  q is recomputed for the K winners in the
+// epilogue from the same record with the same expression, hence bit-identical to the accept test.
+// ---------------------------------------------------------------------------------------------
+constexpr unsigned long long KEY_EMPTY = ~0ull;
+
+__device__ __forceinline__ unsigned long long make_key(float z, int id) {
+    return ((unsigned long long)__float_as_uint(z) << 32) | (unsigned int)id;
+}
+
+template <int KMAX, bool PER_POINT_CUTOFF, bool BLEND>
+__global__ void __launch_bounds__(RASTER_THREADS)
+raster_scatter_kernel(const __grid_constant__ RasterArgs a) {
+    __shared__ unsigned long long s_keys[RASTER_THREADS * KMAX];   // [pixel][k]
+
+    const int S = a.S, B = a.B, K = a.K;
+    const int n = blockIdx.y;
+    const int tile = blockIdx.x;
+    const int ty = tile / B, tx = tile - ty * B;
+    const int tid = threadIdx.x;
+    const int64_t tbase = (int64_t)n * B * B + tile;
+    const int beg = a.tile_offsets[tbase], end = a.tile_offsets[tbase + 1];
+    const int tx0 = tx * RASTER_TILE, ty0 = ty * RASTER_TILE;
+    const int tx1 = min(tx0 + RASTER_TILE, S) - 1, ty1 = min(ty0 + RASTER_TILE, S) - 1;
+    const bool pow2 = (S & (S - 1)) == 0;
+    const float inv_S = 1.0f / (float)S, half_S = 0.5f * (float)S;
+
+    if (beg < end) {
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) s_keys[k * RASTER_THREADS + tid] = KEY_EMPTY;   // coalesced init
+        __syncthreads();
+        for (int j = beg + tid; j < end; j += RASTER_THREADS) {
+            const int id = a.tile_ids[j];
+            const float4 A = __ldg(&a.rec[2 * (int64_t)id]);
+            const float4 Bv = __ldg(&a.rec[2 * (int64_t)id + 1]);
+            if (!(A.z >= 0.0f)) continue;
+            const float cut = PER_POINT_CUTOFF ? __ldg(&a.cutoff[id]) : a.cutoff_uniform;
+            const unsigned long long key = make_key(A.z + 0.0f, id);
+            // conservative pixel-index range of the bbox (exact tests below), clipped to the tile
+            const float fx0 = (A.x - A.w + 1.0f) * half_S - 0.5f, fx1 = (A.x + A.w + 1.0f) * half_S - 0.5f;
+            const float fy0 = (A.y - Bv.x + 1.0f) * half_S - 0.5f, fy1 = (A.y + Bv.x + 1.0f) * half_S - 0.5f;
+            const int x0 = max(tx0, (int)fmaxf(ceilf(fx0) - 1.0f, -1.0f));
+            const int x1 = min(tx1, (int)fminf(floorf(fx1) + 1.0f, (float)S));
+            const int y0 = max(ty0, (int)fmaxf(ceilf(fy0) - 1.0f, -1.0f));
+            const int y1 = min(ty1, (int)fminf(floorf(fy1) + 1.0f, (float)S));
+            for (int yi = y0; yi <= y1; ++yi) {
+                const float dy = pix_to_ndc_fast(yi, S, inv_S, pow2) - A.y;
+                if (fabsf(dy) > Bv.x) continue;
+                unsigned long long *row = s_keys + ((yi - ty0) * RASTER_TILE - tx0) * KMAX;
+                for (int xi = x0; xi <= x1; ++xi) {
+                    unsigned long long *slot = row + xi * KMAX;
+                    if (key >= slot[KMAX - 1]) continue;             // cannot enter this pixel's list
+                    const float dx = pix_to_ndc_fast(xi, S, inv_S, pow2) - A.x;
+                    if (fabsf(dx) > A.w) continue;
+                    // rasterize_points.cu:94 -- same expression tree for q as the reference
+                    const float qv = Bv.y * dx * dx + Bv.z * dx * dy + Bv.w * dy * dy;
+                    if (qv > cut) continue;
+                    unsigned long long carry = key;
+#pragma unroll
+                    for (int k = 0; k < KMAX; ++k) {
+                        if (carry < slot[k]) {
+                            const unsigned long long old = atomicMin(&slot[k], carry);
+                            carry = old > carry ? old : carry;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- epilogue: one thread per pixel ----
+    const int xi = tx0 + (tid & (RASTER_TILE - 1));
+    const int yi = ty0 + (tid >> 4);
+    if (xi >= S || yi >= S) return;
+    const int64_t pix = ((int64_t)n * S + (S - 1 - yi)) * S + (S - 1 - xi);
+    const float xf = pix_to_ndc_fast(xi, S, inv_S, pow2);
+    const float yf = pix_to_ndc_fast(yi, S, inv_S, pow2);
+    float fz[KMAX], fq[KMAX];
+    int fid[KMAX];
+    bool emit[KMAX];
+    bool open = beg < end;
+    float z0 = 0.f;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+        fz[k] = -1.0f;
+        fq[k] = -1.0f;
+        fid[k] = -1;
+        emit[k] = false;
+        if (open && k < K) {
+            const unsigned long long key = s_keys[(tid * KMAX) + k];
+            if (key == KEY_EMPTY) {
+                open = false;
+            } else {
+                const float z = __uint_as_float((unsigned int)(key >> 32));
+                if (k == 0) z0 = z;
+                if (z - z0 > a.depth_merge) {   // rasterize_points.cu:586-595
+                    open = false;
+                } else {
+                    const int id = (int)(unsigned int)(key & 0xffffffffull);
+                    const float4 A = __ldg(&a.rec[2 * (int64_t)id]);
+                    const float4 Bv = __ldg(&a.rec[2 * (int64_t)id + 1]);
+                    const float dx = xf - A.x, dy = yf - A.y;
+                    fz[k] = z;
+                    fid[k] = id;
+                    fq[k] = Bv.y * dx * dx + Bv.z * dx * dy + Bv.w * dy * dy;
+                    emit[k] = true;
+                }
+            }
+        }
+    }
+    const bool any = (beg < end) && (s_keys[tid * KMAX] != KEY_EMPTY);
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+        if (k < K) {
+            a.idx[pix * K + k] = fid[k];
+            if (a.zbuf) a.zbuf[pix * K + k] = fz[k];
+            if (a.qvalue) a.qvalue[pix * K + k] = fq[k];
+        }
+    }
+    const float occ = any ? 1.0f : 0.0f;
+    if (a.occ) a.occ[pix] = occ;
+    if (BLEND) {
+        float w[KMAX];
+        float wsum = 0.f, r = 0.f, g = 0.f, b = 0.f;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+            w[k] = 0.f;
+            if (emit[k]) {
+                const int id = fid[k];
+                w[k] = expf(-0.5f * fq[k]) * __ldg(&a.scaler[id]);
+                const float *c = a.colours + (int64_t)id * 3;
+                r += w[k] * __ldg(c + 0);
+                g += w[k] * __ldg(c + 1);
+                b += w[k] * __ldg(c + 2);
+                wsum += w[k];
+                if (a.visible) a.visible[id] = 1;
+            }
+        }
+        const float inv = 1.0f / fmaxf(wsum, 1e-4f);
+        reinterpret_cast<float4 *>(a.image)[pix] = make_float4(r * inv, g * inv, b * inv, occ);
+        if (a.weights) {
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k)
+                if (k < K) a.weights[pix * K + k] = w[k] * inv;
+        }
+    }
+}
+
+template <int KMAX>
+static int launch_scatter(dss_ctx *ctx, const RasterArgs &a, cudaStream_t st) {
+    dim3 grid((unsigned)(a.B * a.B), (unsigned)a.N);
+    StageScope prof(ctx, ST_RASTER_FWD, st);
+    const bool blend = a.image != nullptr;
+    if (blend) {
+        if (a.cutoff)
+            raster_scatter_kernel<KMAX, true, true><<<grid, RASTER_THREADS, 0, st>>>(a);
+        else
+            raster_scatter_kernel<KMAX, false, true><<<grid, RASTER_THREADS, 0, st>>>(a);
+    } else {
+        if (a.cutoff)
+            raster_scatter_kernel<KMAX, true, false><<<grid, RASTER_THREADS, 0, st>>>(a);
+        else
+            raster_scatter_kernel<KMAX, false, false><<<grid, RASTER_THREADS, 0, st>>>(a);
+    }
+    DSS_LAUNCH_CHECK(ctx);
+    return DSS_OK;
+}
+
 template <int KMAX>
 static int launch_raster(dss_ctx *ctx, const RasterArgs &a, cudaStream_t st) {
     dim3 grid((unsigned)(a.B * a.B), (unsigned)a.N);
@@ -203,6 +382,10 @@ static int launch_raster(dss_ctx *ctx, const RasterArgs &a, cudaStream_t st) {
 
 int raster_forward(dss_ctx *ctx, const RasterArgs &a, cudaStream_t st) {
     if (a.N <= 0 || a.S <= 0) return DSS_OK;
+    if (!a.force_pixel_parallel) {
+        if (a.K <= 5) return launch_scatter<5>(ctx, a, st);
+        if (a.K <= 8) return launch_scatter<8>(ctx, a, st);
+    }
     if (a.K <= 5) return launch_raster<5>(ctx, a, st);
     if (a.K <= 8) return launch_raster<8>(ctx, a, st);
     if (a.K <= 16) return launch_raster<16>(ctx, a, st);
