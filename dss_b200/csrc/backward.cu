@@ -204,7 +204,7 @@ __host__ __device__ __forceinline__ int occ_halo(float r, int S) { return (int)c
 __host__ __device__ __forceinline__ bool occ_tile_fits(float r, int S, int smem_bytes) {
     if (!(r >= 0.0f) || !(r < 4.0f) || smem_bytes <= 0) return false;
     const int side = OCC_TILE + 2 * occ_halo(r, S);
-    return (size_t)side * side * sizeof(float) <= (size_t)smem_bytes;
+    return (size_t)(side * side + 2 * side) * sizeof(float) <= (size_t)smem_bytes;
 }
 
 __device__ __forceinline__ int centre_tile(float px, float py, int S, int OB) {
@@ -276,8 +276,19 @@ occ_tile_kernel(const float4 *__restrict__ rec, const float *__restrict__ rs, co
     const float r = rs[n];
     if (!occ_tile_fits(r, S, smem_bytes)) return;
     const int64_t tb = (int64_t)n * OB * OB + tile;
-    const int beg = tile_offsets[tb], end = tile_offsets[tb + 1];
+    int beg = tile_offsets[tb], end = tile_offsets[tb + 1];
     if (beg == end) return;
+    {
+        // a tile's list is split over up to gridDim.z CTAs (>= 64 splats each) so that dense tiles do not
+        // serialise on one CTA; every CTA stages the (small) window itself
+        const int count = end - beg;
+        const int parts = min((int)gridDim.z, (count + 63) / 64);
+        if ((int)blockIdx.z >= parts) return;
+        const int per = (count + parts - 1) / parts;
+        beg += (int)blockIdx.z * per;
+        end = min(end, beg + per);
+        if (beg >= end) return;
+    }
     const int R = occ_halo(r, S);
     const int side = OCC_TILE + 2 * R;
     const int ty = tile / OB, tx = tile - ty * OB;
@@ -286,21 +297,28 @@ occ_tile_kernel(const float4 *__restrict__ rec, const float *__restrict__ rs, co
     for (int i = threadIdx.x; i < side * side; i += OCC_TILE_THREADS) {
         const int wy = i / side, wx = i - wy * side;
         const int xi = wx0 + wx, yi = wy0 + wy;
-        float g = 0.0f;
+        float g = 0.0f;   // zero outside the image: such pixels then drop out of the sum by the g != 0 rule
         if (xi >= 0 && xi < S && yi >= 0 && yi < S)
             g = __ldg(gview + ((int64_t)(S - 1 - yi) * S + (S - 1 - xi)) * pix_stride);
         s_g[i] = g;
     }
+    // exact pixel-centre NDC coordinates of the window's columns / rows (the reference's PixToNdc, division
+    // included, evaluated once per CTA instead of once per pair)
+    float *s_xf = s_g + side * side, *s_yf = s_xf + side;
+    for (int i = threadIdx.x; i < side; i += OCC_TILE_THREADS) {
+        s_xf[i] = pix_to_ndc(wx0 + i, S);
+        s_yf[i] = pix_to_ndc(wy0 + i, S);
+    }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float r2 = r * r;
-    const bool pow2 = (S & (S - 1)) == 0;
-    const float inv_S = 1.0f / (float)S, half_S = 0.5f * (float)S;
+    const float half_S = 0.5f * (float)S;
     constexpr unsigned FULL = 0xffffffffu;
     // Lane <-> window column, loop over window rows.  dx (hence dx^2 and the x half of the bbox test) is
     // a per-lane constant of the splat, dy is shared by the row, and since dx is constant along a column
     //     sum_rows dx * w = dx * sum_rows w ,   w = g / max(d2, 1e-10)
-    // each pair costs one reciprocal, one add and one fma.  Narrow windows pack several splats per warp.
+    // each pair costs one reciprocal, one add and one fma, branch-free.  Narrow windows pack several
+    // splats per warp (8 or 16 lanes each).
     const int Rw = R - 1;                       // per-splat window half-width in pixels (covers the disc)
     const int Wwin = 2 * Rw + 1;
     const int lpp = Wwin <= 8 ? 8 : (Wwin <= 16 ? 16 : 32);   // lanes per splat
@@ -319,34 +337,38 @@ occ_tile_kernel(const float4 *__restrict__ rec, const float *__restrict__ rs, co
             rx = A.w;
             ry = __ldg(&rec[2 * (int64_t)p + 1]).x;
         }
-        const int cx = min(max((int)floorf((px + 1.0f) * half_S), 0), S - 1);
-        const int cy = min(max((int)floorf((py + 1.0f) * half_S), 0), S - 1);
+        // window origin in staged-window coordinates (always inside: the halo R = Rw + 1 covers it)
+        const int cx = min(max((int)floorf((px + 1.0f) * half_S), tx * OCC_TILE), tx * OCC_TILE + OCC_TILE - 1);
+        const int cy = min(max((int)floorf((py + 1.0f) * half_S), ty * OCC_TILE), ty * OCC_TILE + OCC_TILE - 1);
+        const int ox = cx - Rw - wx0, oy = cy - Rw - wy0;
         float gx = 0.f, gy = 0.f;
         for (int cb = 0; cb < Wwin; cb += lpp) {            // column blocks (one unless the window is > 32 wide)
-            const int xi = cx - Rw + cb + gl;
-            const bool col_ok = have && (cb + gl < Wwin) && xi >= 0 && xi < S;
-            const float dx = pix_to_ndc_fast(xi, S, inv_S, pow2) - px;
+            const bool col_ok = have && (cb + gl < Wwin);
+            const int sx = col_ok ? ox + cb + gl : ox;      // inactive lanes read a valid column, result dropped
+            const float dx = s_xf[sx] - px;
             const float dx2 = dx * dx;
             const bool out_x = fabsf(dx) > rx;
-            const float *col = s_g + (xi - wx0);
+            const float *col = s_g + oy * side + sx;
+            const float *yfp = s_yf + oy;
             float sw = 0.f, swy = 0.f;
+#pragma unroll 4
             for (int j = 0; j < Wwin; ++j) {
-                const int yi = cy - Rw + j;
-                if (col_ok && yi >= 0 && yi < S) {
-                    const float g = col[(yi - wy0) * side];
-                    const float dy = pix_to_ndc_fast(yi, S, inv_S, pow2) - py;
-                    const float d2 = fmaf(dy, dy, dx2);
-                    const bool outside = out_x || (fabsf(dy) > ry);
-                    // rasterize_points_backward.cu:156-172
-                    if (g != 0.0f && !(d2 > r2) && !(g > 0.0f && outside)) {
-                        const float w = g * __frcp_rn(fmaxf(d2, 1e-10f));
-                        sw += w;
-                        swy = fmaf(w, dy, swy);
-                    }
-                }
+                const float g = col[j * side];
+                const float dy = yfp[j] - py;
+                const float d2 = fmaf(dy, dy, dx2);
+                const bool outside = out_x || (fabsf(dy) > ry);
+                // rasterize_points_backward.cu:156-172
+                const bool use = (g != 0.0f) && !(d2 > r2) && !(g > 0.0f && outside);
+                float inv;
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(fmaxf(d2, 1e-10f)));
+                const float w = use ? g * inv : 0.0f;
+                sw += w;
+                swy = fmaf(w, dy, swy);
             }
-            gx = fmaf(dx, sw, gx);
-            gy += swy;
+            if (col_ok) {
+                gx = fmaf(dx, sw, gx);
+                gy += swy;
+            }
         }
         for (int d = lpp >> 1; d > 0; d >>= 1) {
             gx += __shfl_xor_sync(FULL, gx, d);
@@ -471,7 +493,7 @@ int occ_backward(dss_ctx *ctx, const float4 *rec, const uint8_t *visible, const 
     int smem = 64 * 1024;
     if (hint > 0.0f && hint < 4.0f) {
         const int side = OCC_TILE + 2 * (occ_halo(hint * 1.25f, S) + 1);
-        smem = side * side * (int)sizeof(float);
+        smem = (side * side + 2 * side) * (int)sizeof(float);
         if (smem < 16 * 1024) smem = 16 * 1024;
         if (smem > 200 * 1024) smem = 200 * 1024;
     }
@@ -501,7 +523,7 @@ int occ_backward(dss_ctx *ctx, const float4 *rec, const uint8_t *visible, const 
         DSS_CUDA_TRY(cudaMemsetAsync(grad_xy, 0, (size_t)Ptot * 2 * sizeof(float), st));
         if (smem > 48 * 1024)
             DSS_CUDA_TRY(cudaFuncSetAttribute(occ_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        dim3 tgrid((unsigned)(OB * OB), N);
+        dim3 tgrid((unsigned)(OB * OB), N, 32);
         occ_tile_kernel<<<tgrid, OCC_TILE_THREADS, smem, st>>>(rec, rs, grad_occ, pix_stride, pix_offset, offsets, ids,
                                                               S, OB, smem, reinterpret_cast<float2 *>(grad_xy));
         DSS_LAUNCH_CHECK(ctx);
