@@ -61,7 +61,8 @@ class PointsRasterizationSettings:
         self.antialiasing_sigma = antialiasing_sigma
 
 
-def _splat_params(rs: PointsRasterizationSettings, cameras, **kwargs) -> SplatParams:
+def _splat_params(rs: PointsRasterizationSettings, cameras, kwargs=None) -> SplatParams:
+    kwargs = kwargs or {}
     znear = getattr(cameras, "znear", kwargs.get("znear", 1.0))
     zfar = getattr(cameras, "zfar", kwargs.get("zfar", 100.0))
     f = lambda v: float(v.reshape(-1)[0]) if torch.is_tensor(v) else float(v)
@@ -163,7 +164,7 @@ class SurfaceSplatting(nn.Module):
         normals = point_clouds.normals_packed()
         if normals is None:
             raise ValueError("surface splatting needs point normals")
-        prm = _splat_params(rs, cameras, **kwargs)
+        prm = _splat_params(rs, cameras, kwargs)
         return preprocess_points(point_clouds.points_packed(), normals, proj.to(dev), view.to(dev), h.to(dev), prm,
                                  first_idx=point_clouds.cloud_to_packed_first_idx(),
                                  num_points=point_clouds.num_points_per_cloud(), shared_cloud=False)

@@ -59,7 +59,7 @@ class SurfaceSplattingRenderer(nn.Module):
         point_clouds = rast._prepare_clouds(point_clouds, kwargs.get("point_clouds_filter", None), cameras)
         dev = point_clouds.device
         proj, view = camera_matrices(cameras)
-        prm = _splat_params(rs, cameras, **kwargs)
+        prm = _splat_params(rs, cameras, kwargs)
         with torch.no_grad():
             h = kwargs.get("Vrk_h", None)
             if h is None:
