@@ -53,6 +53,7 @@ _SIGNATURES = {
     "dss_profile_num_stages": (C.c_int, []),
     "dss_profile_stage_name": (C.c_char_p, [C.c_int]),
     "dss_profile_read": (C.c_int, [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "dss_debug_raster_stats": (C.c_int, [vp, C.c_int, C.POINTER(C.c_uint64)]),
     "dss_exclusive_scan_i32": (C.c_int, [vp, vp, vp, C.c_int64, vp]),
     "dss_grid_insert_points_2d": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
     "dss_grid_counting_sort_2d": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
@@ -149,6 +150,14 @@ def profile_read(device=None):
         check(lib.dss_profile_read(ctx(device), i, C.byref(ms), C.byref(n)), "dss_profile_read")
         out[lib.dss_profile_stage_name(i).decode()] = (ms.value, n.value)
     return out
+
+
+def raster_stats(enable, device=None):
+    """debug counters of the sliced rasterizer accumulated since they were last enabled (see the header)."""
+    out = (C.c_uint64 * 8)()
+    check(load().dss_debug_raster_stats(ctx(device), int(bool(enable)), out), "dss_debug_raster_stats")
+    names = ["entries_scanned", "survivors", "pixel_tests", "accepted", "slices_skipped", "slices_visited"]
+    return dict(zip(names, [int(v) for v in out[:6]]))
 
 
 def scratch_bytes(device=None):

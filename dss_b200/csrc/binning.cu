@@ -91,6 +91,58 @@ __device__ __forceinline__ BinRect splat_bin_rect(const float4 A, const float ry
 }
 
 // ---------------------------------------------------------------------------------------------
+// Depth slices.  Tile lists are ordered front to back in NS coarse slices of the view's depth range so
+// that the rasterizer can stop as soon as every pixel of a tile already holds K nearer fragments.
+// zrange[n] = {zmin, zmax} over the renderable (z >= 0) splats of view n.  Slice s covers
+// [slice_bound(s), slice_bound(s+1)); depth_slice() guarantees slice_bound(slice) <= z.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+zrange_kernel(const float4 *__restrict__ rec, const int64_t *__restrict__ first_idx,
+              const int64_t *__restrict__ num_points, int64_t P0_shared, int32_t *__restrict__ zrange) {
+    const int n = blockIdx.y;
+    const ViewRange vr = view_range(first_idx, num_points, n, P0_shared);
+    int zmin = 0x7f7fffff, zmax = 0;   // float bits; non-negative floats order like ints
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < vr.count;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const float z = __ldg(&rec[2 * (vr.first + i)]).z;
+        if (z >= 0.0f && z < 3.0e38f) {
+            const int b = __float_as_int(z + 0.0f);
+            zmin = min(zmin, b);
+            zmax = max(zmax, b);
+        }
+    }
+    zmin = __reduce_min_sync(0xffffffffu, zmin);
+    zmax = __reduce_max_sync(0xffffffffu, zmax);
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&zrange[2 * n], zmin);
+        atomicMax(&zrange[2 * n + 1], zmax);
+    }
+}
+
+__global__ void zrange_init_kernel(int32_t *zrange, int N) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) {
+        zrange[2 * i] = 0x7f7fffff;
+        zrange[2 * i + 1] = 0;
+    }
+}
+
+int compute_zrange(dss_ctx *ctx, const float4 *rec, const int64_t *first_idx, const int64_t *num_points, int N,
+                   int64_t P0, float *zrange, cudaStream_t st) {
+    StageScope prof(ctx, ST_BIN_COUNT, st);
+    zrange_init_kernel<<<(N + 127) / 128, 128, 0, st>>>(reinterpret_cast<int32_t *>(zrange), N);
+    DSS_LAUNCH_CHECK(ctx);
+    if (P0 > 0) {
+        int64_t b = (P0 + 2047) / 2048;
+        if (b > ctx->sm_count * 4) b = ctx->sm_count * 4;
+        dim3 grid((unsigned)b, N);
+        zrange_kernel<<<grid, 256, 0, st>>>(rec, first_idx, num_points, P0, reinterpret_cast<int32_t *>(zrange));
+        DSS_LAUNCH_CHECK(ctx);
+    }
+    return DSS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // count / scatter with block-level aggregation.  A block owns a contiguous chunk of BIN_ITEMS*256
 // splats of one view, keeps the per-tile histogram of that chunk in shared memory and touches global
 // memory with ONE atomic per (block, non-empty tile) instead of one per (splat, tile): the per-tile
@@ -109,11 +161,12 @@ __device__ __forceinline__ int2 pack_rect(const BinRect &r) {
 template <bool SMEM>
 __global__ void __launch_bounds__(BIN_THREADS)
 bin_count_kernel(const float4 *__restrict__ rec, const int64_t *__restrict__ first_idx,
-                 const int64_t *__restrict__ num_points, int64_t P0_shared, int S, int bin, int B,
-                 int32_t *__restrict__ counts) {
+                 const int64_t *__restrict__ num_points, int64_t P0_shared, int S, int bin, int B, int NS,
+                 const float *__restrict__ zrange, int32_t *__restrict__ counts) {
     extern __shared__ int32_t s_hist[];
     const int n = blockIdx.y;
-    const int nt = B * B;
+    const int nt = B * B * NS;
+    const SliceMap sm = make_slice_map(zrange, n, NS);
     const ViewRange vr = view_range(first_idx, num_points, n, P0_shared);
     const int64_t chunk0 = (int64_t)blockIdx.x * BIN_CHUNK;
     if (chunk0 >= vr.count) return;
@@ -131,8 +184,12 @@ bin_count_kernel(const float4 *__restrict__ rec, const int64_t *__restrict__ fir
         const float ry = __ldg(&rec[2 * p + 1]).x;
         const BinRect r = splat_bin_rect(A, ry, bin, S, B);
         if (r.empty) continue;
+        const int sl = depth_slice(sm, A.z);
         for (int by = r.y0; by <= r.y1; ++by)
-            for (int bx = r.x0; bx <= r.x1; ++bx) atomicAdd(SMEM ? &s_hist[by * B + bx] : &cnt[by * B + bx], 1);
+            for (int bx = r.x0; bx <= r.x1; ++bx) {
+                const int key = (by * B + bx) * NS + sl;
+                atomicAdd(SMEM ? &s_hist[key] : &cnt[key], 1);
+            }
     }
     if (SMEM) {
         __syncthreads();
@@ -147,11 +204,12 @@ bin_count_kernel(const float4 *__restrict__ rec, const int64_t *__restrict__ fir
 template <bool SMEM>
 __global__ void __launch_bounds__(BIN_THREADS)
 bin_scatter_kernel(const float4 *__restrict__ rec, const int64_t *__restrict__ first_idx,
-                   const int64_t *__restrict__ num_points, int64_t P0_shared, int S, int bin, int B,
-                   int32_t *__restrict__ cursors, int32_t *__restrict__ ids) {
+                   const int64_t *__restrict__ num_points, int64_t P0_shared, int S, int bin, int B, int NS,
+                   const float *__restrict__ zrange, int32_t *__restrict__ cursors, int32_t *__restrict__ ids) {
     extern __shared__ int32_t s_hist[];
     const int n = blockIdx.y;
-    const int nt = B * B;
+    const int nt = B * B * NS;
+    const SliceMap sm = make_slice_map(zrange, n, NS);
     const ViewRange vr = view_range(first_idx, num_points, n, P0_shared);
     const int64_t chunk0 = (int64_t)blockIdx.x * BIN_CHUNK;
     if (chunk0 >= vr.count) return;
@@ -161,9 +219,11 @@ bin_scatter_kernel(const float4 *__restrict__ rec, const int64_t *__restrict__ f
         __syncthreads();
     }
     int2 rect[BIN_ITEMS];
+    int slice[BIN_ITEMS];
 #pragma unroll
     for (int j = 0; j < BIN_ITEMS; ++j) {
         rect[j] = make_int2(-1, -1);
+        slice[j] = 0;
         const int64_t i = chunk0 + j * BIN_THREADS + threadIdx.x;
         if (i < vr.count) {
             const int64_t p = vr.first + i;
@@ -172,12 +232,14 @@ bin_scatter_kernel(const float4 *__restrict__ rec, const int64_t *__restrict__ f
             const BinRect r = splat_bin_rect(A, ry, bin, S, B);
             rect[j] = pack_rect(r);
             if (!r.empty) {
+                slice[j] = depth_slice(sm, A.z);
                 for (int by = r.y0; by <= r.y1; ++by)
                     for (int bx = r.x0; bx <= r.x1; ++bx) {
+                        const int key = (by * B + bx) * NS + slice[j];
                         if (SMEM) {
-                            atomicAdd(&s_hist[by * B + bx], 1);
+                            atomicAdd(&s_hist[key], 1);
                         } else {
-                            const int slot = atomicAdd(&cur[by * B + bx], 1);
+                            const int slot = atomicAdd(&cur[key], 1);
                             ids[slot] = (int32_t)p;
                         }
                     }
@@ -199,7 +261,7 @@ bin_scatter_kernel(const float4 *__restrict__ rec, const int64_t *__restrict__ f
         const int32_t p = (int32_t)(vr.first + chunk0 + j * BIN_THREADS + threadIdx.x);
         for (int by = y0; by <= y1; ++by)
             for (int bx = x0; bx <= x1; ++bx) {
-                const int slot = atomicAdd(&s_hist[by * B + bx], 1);
+                const int slot = atomicAdd(&s_hist[(by * B + bx) * NS + slice[j]], 1);
                 ids[slot] = p;
             }
     }
@@ -220,22 +282,30 @@ static int prepare_smem(Kern kern, size_t bytes) {
     return DSS_OK;
 }
 
-// count + scan.  offsets must have N*B*B + 1 entries; counts N*B*B + 1 (last stays 0).
+// Number of depth slices such that the per-block histogram (B*B*NS ints) fits in shared memory.
+int choose_depth_slices(int B) {
+    int ns = 16;
+    while (ns > 1 && (int64_t)B * B * ns > 32 * 1024) ns >>= 1;   // <= 128 KB of histogram
+    return ns;
+}
+
+// count + scan.  counts / offsets have N*B*B*NS + 1 entries (the last count stays 0).
 int bin_count_and_scan(dss_ctx *ctx, const float4 *rec, const int64_t *first_idx, const int64_t *num_points,
-                       int N, int64_t P0, int S, int bin, int32_t *counts, int32_t *offsets, cudaStream_t st) {
+                       int N, int64_t P0, int S, int bin, int NS, const float *zrange, int32_t *counts,
+                       int32_t *offsets, cudaStream_t st) {
     const int B = 1 + (S - 1) / bin;
-    const int64_t nb = (int64_t)N * B * B;
+    const int64_t nb = (int64_t)N * B * B * NS;
     DSS_CUDA_TRY(cudaMemsetAsync(counts, 0, (size_t)(nb + 1) * sizeof(int32_t), st));
     if (P0 > 0) {
         dim3 grid((unsigned)((P0 + BIN_CHUNK - 1) / BIN_CHUNK), N);
         StageScope prof(ctx, ST_BIN_COUNT, st);
-        if (B * B <= BIN_MAX_SMEM_TILES && B < 32768) {
-            const size_t smem = (size_t)B * B * sizeof(int32_t);
+        if ((int64_t)B * B * NS <= BIN_MAX_SMEM_TILES && B < 32768) {
+            const size_t smem = (size_t)B * B * NS * sizeof(int32_t);
             int rc = prepare_smem(bin_count_kernel<true>, smem);
             if (rc) return rc;
-            bin_count_kernel<true><<<grid, BIN_THREADS, smem, st>>>(rec, first_idx, num_points, P0, S, bin, B, counts);
+            bin_count_kernel<true><<<grid, BIN_THREADS, smem, st>>>(rec, first_idx, num_points, P0, S, bin, B, NS, zrange, counts);
         } else {
-            bin_count_kernel<false><<<grid, BIN_THREADS, 0, st>>>(rec, first_idx, num_points, P0, S, bin, B, counts);
+            bin_count_kernel<false><<<grid, BIN_THREADS, 0, st>>>(rec, first_idx, num_points, P0, S, bin, B, NS, zrange, counts);
         }
         DSS_LAUNCH_CHECK(ctx);
     }
@@ -243,21 +313,21 @@ int bin_count_and_scan(dss_ctx *ctx, const float4 *rec, const int64_t *first_idx
 }
 
 int bin_scatter(dss_ctx *ctx, const float4 *rec, const int64_t *first_idx, const int64_t *num_points, int N,
-                int64_t P0, int S, int bin, const int32_t *offsets, int32_t *cursors, int32_t *ids,
-                cudaStream_t st) {
+                int64_t P0, int S, int bin, int NS, const float *zrange, const int32_t *offsets, int32_t *cursors,
+                int32_t *ids, cudaStream_t st) {
     const int B = 1 + (S - 1) / bin;
-    const int64_t nb = (int64_t)N * B * B;
+    const int64_t nb = (int64_t)N * B * B * NS;
     DSS_CUDA_TRY(cudaMemcpyAsync(cursors, offsets, (size_t)nb * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
     if (P0 > 0) {
         dim3 grid((unsigned)((P0 + BIN_CHUNK - 1) / BIN_CHUNK), N);
         StageScope prof(ctx, ST_BIN_SCATTER, st);
-        if (B * B <= BIN_MAX_SMEM_TILES && B < 32768) {
-            const size_t smem = (size_t)B * B * sizeof(int32_t);
+        if ((int64_t)B * B * NS <= BIN_MAX_SMEM_TILES && B < 32768) {
+            const size_t smem = (size_t)B * B * NS * sizeof(int32_t);
             int rc = prepare_smem(bin_scatter_kernel<true>, smem);
             if (rc) return rc;
-            bin_scatter_kernel<true><<<grid, BIN_THREADS, smem, st>>>(rec, first_idx, num_points, P0, S, bin, B, cursors, ids);
+            bin_scatter_kernel<true><<<grid, BIN_THREADS, smem, st>>>(rec, first_idx, num_points, P0, S, bin, B, NS, zrange, cursors, ids);
         } else {
-            bin_scatter_kernel<false><<<grid, BIN_THREADS, 0, st>>>(rec, first_idx, num_points, P0, S, bin, B, cursors, ids);
+            bin_scatter_kernel<false><<<grid, BIN_THREADS, 0, st>>>(rec, first_idx, num_points, P0, S, bin, B, NS, zrange, cursors, ids);
         }
         DSS_LAUNCH_CHECK(ctx);
     }
@@ -354,7 +424,7 @@ int dss_rasterize_coarse(dss_ctx *ctx, const float *points, const float *radii, 
     if ((rc = ctx_get(ctx, BUF_RECORDS, (size_t)(2 * (P > 0 ? P : 1)), &rec))) return rc;
     if ((rc = ctx_get(ctx, BUF_TILE_COUNTS, (size_t)(nb + 1), &counts))) return rc;
     if ((rc = pack_records(ctx, points, radii, nullptr, P, rec, st))) return rc;
-    if ((rc = bin_count_and_scan(ctx, rec, first_idx, num_points, N, P, S, bin_size, counts, bin_offsets, st)))
+    if ((rc = bin_count_and_scan(ctx, rec, first_idx, num_points, N, P, S, bin_size, 1, nullptr, counts, bin_offsets, st)))
         return rc;
     DSS_CUDA_TRY(cudaMemcpyAsync(ctx->h_pinned, bin_offsets + nb, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     DSS_CUDA_TRY(cudaStreamSynchronize(st));
@@ -365,7 +435,7 @@ int dss_rasterize_coarse(dss_ctx *ctx, const float *points, const float *radii, 
         return DSS_E_CAPACITY;
     }
     if (total == 0) return DSS_OK;
-    return bin_scatter(ctx, rec, first_idx, num_points, N, P, S, bin_size, bin_offsets, counts, bin_ids, st);
+    return bin_scatter(ctx, rec, first_idx, num_points, N, P, S, bin_size, 1, nullptr, bin_offsets, counts, bin_ids, st);
 }
 
 }  // extern "C"

@@ -53,6 +53,8 @@ enum BufId {
     BUF_RS,
     BUF_GRADXY,
     BUF_CUTOFF,
+    BUF_ZRANGE,
+    BUF_STATS,
     NUM_BUFS
 };
 
@@ -82,6 +84,7 @@ struct dss_ctx {
     dss::ProfPending *pending;
     int n_pending, cap_pending;
     int open[8], n_open;
+    int raster_stats;   // debug: accumulate raster work counters
     double stage_ms[dss::NUM_STAGES];
     int64_t stage_calls[dss::NUM_STAGES];
 };

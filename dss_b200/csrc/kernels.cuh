@@ -11,12 +11,49 @@ int exclusive_scan_i32(dss_ctx *ctx, const int32_t *in, int32_t *out, int64_t n,
 int pack_records(dss_ctx *ctx, const float *points, const float *radii, const float *ellipse, int64_t P,
                  float4 *rec, cudaStream_t st);
 
+int choose_depth_slices(int B);
+int compute_zrange(dss_ctx *ctx, const float4 *rec, const int64_t *first_idx, const int64_t *num_points, int N,
+                   int64_t P0, float *zrange, cudaStream_t st);
+
 int bin_count_and_scan(dss_ctx *ctx, const float4 *rec, const int64_t *first_idx, const int64_t *num_points,
-                       int N, int64_t P0, int S, int bin, int32_t *counts, int32_t *offsets, cudaStream_t st);
+                       int N, int64_t P0, int S, int bin, int NS, const float *zrange, int32_t *counts,
+                       int32_t *offsets, cudaStream_t st);
 
 int bin_scatter(dss_ctx *ctx, const float4 *rec, const int64_t *first_idx, const int64_t *num_points, int N,
-                int64_t P0, int S, int bin, const int32_t *offsets, int32_t *cursors, int32_t *ids,
-                cudaStream_t st);
+                int64_t P0, int S, int bin, int NS, const float *zrange, const int32_t *offsets, int32_t *cursors,
+                int32_t *ids, cudaStream_t st);
+
+// Depth slicing shared by the binning and raster kernels (identical arithmetic on both sides).
+struct SliceMap {
+    float zmin, dz, inv_dz;
+    int NS;
+};
+__device__ __forceinline__ float slice_bound(const SliceMap &m, int s) { return fmaf((float)s, m.dz, m.zmin); }
+__device__ __forceinline__ SliceMap make_slice_map(const float *zrange, int n, int NS) {
+    SliceMap m;
+    m.NS = NS;
+    m.zmin = 0.f;
+    m.dz = 0.f;
+    m.inv_dz = 0.f;
+    if (NS > 1 && zrange) {
+        const float z0 = zrange[2 * n], z1 = zrange[2 * n + 1];
+        if (z1 > z0) {
+            m.zmin = z0;
+            m.dz = (z1 - z0) / (float)NS;
+            m.inv_dz = 1.0f / m.dz;
+        }
+    }
+    return m;
+}
+// slice index with slice_bound(slice) <= z guaranteed (estimate + exact fix-up)
+__device__ __forceinline__ int depth_slice(const SliceMap &m, float z) {
+    if (m.NS <= 1 || !(m.dz > 0.f)) return 0;
+    int s = (int)((z - m.zmin) * m.inv_dz);
+    s = max(0, min(m.NS - 1, s));
+    while (s > 0 && z < slice_bound(m, s)) --s;
+    while (s < m.NS - 1 && z >= slice_bound(m, s + 1)) ++s;
+    return s;
+}
 
 struct RasterArgs {
     const float4 *rec;        // 2 per splat
@@ -25,6 +62,8 @@ struct RasterArgs {
     const int32_t *tile_offsets;  // (N*B*B + 1)
     const int32_t *tile_ids;
     int N, S, K, B;
+    int NS;                       // depth slices per tile list
+    const float *zrange;          // (N,2) depth range per view (NS > 1)
     float depth_merge;
     // outputs
     int32_t *idx;
@@ -38,6 +77,7 @@ struct RasterArgs {
     float *weights;        // (N,S,S,K)
     uint8_t *visible;      // (P,) must be zeroed by the caller
     int force_pixel_parallel;  // testing: use the pixel-parallel kernel even for K <= 8
+    unsigned long long *stats; // optional debug counters (dss_debug_raster_stats) or nullptr
 };
 
 int raster_forward(dss_ctx *ctx, const RasterArgs &a, cudaStream_t st);

@@ -67,8 +67,8 @@ raster_fwd_kernel(const __grid_constant__ RasterArgs a) {
     }
     float thresh = CUDART_INF_F;  // warp-wide max of the KMAX-th nearest depth
 
-    const int64_t tbase = (int64_t)n * B * B + tile;
-    const int beg = a.tile_offsets[tbase], end = a.tile_offsets[tbase + 1];
+    const int64_t tbase = ((int64_t)n * B * B + tile) * a.NS;
+    const int beg = a.tile_offsets[tbase], end = a.tile_offsets[tbase + a.NS];
 
     for (int base = beg; base < end; base += RASTER_CHUNK) {
         const int cnt = min(RASTER_CHUNK, end - base);
@@ -201,68 +201,13 @@ __device__ __forceinline__ unsigned long long make_key(float z, int id) {
     return ((unsigned long long)__float_as_uint(z) << 32) | (unsigned int)id;
 }
 
-template <int KMAX, bool PER_POINT_CUTOFF, bool BLEND>
-__global__ void __launch_bounds__(RASTER_THREADS)
-raster_scatter_kernel(const __grid_constant__ RasterArgs a) {
-    __shared__ unsigned long long s_keys[RASTER_THREADS * KMAX];   // [pixel][k]
-
-    const int S = a.S, B = a.B, K = a.K;
-    const int n = blockIdx.y;
-    const int tile = blockIdx.x;
-    const int ty = tile / B, tx = tile - ty * B;
+template <int KMAX, bool BLEND>
+__device__ __forceinline__ void raster_epilogue(const RasterArgs &a, const unsigned long long *s_keys, bool tile_has_entries,
+                                                int n, int tx0, int ty0, bool pow2, float inv_S) {
+    const int S = a.S, K = a.K;
     const int tid = threadIdx.x;
-    const int64_t tbase = (int64_t)n * B * B + tile;
-    const int beg = a.tile_offsets[tbase], end = a.tile_offsets[tbase + 1];
-    const int tx0 = tx * RASTER_TILE, ty0 = ty * RASTER_TILE;
-    const int tx1 = min(tx0 + RASTER_TILE, S) - 1, ty1 = min(ty0 + RASTER_TILE, S) - 1;
-    const bool pow2 = (S & (S - 1)) == 0;
-    const float inv_S = 1.0f / (float)S, half_S = 0.5f * (float)S;
-
-    if (beg < end) {
-#pragma unroll
-        for (int k = 0; k < KMAX; ++k) s_keys[k * RASTER_THREADS + tid] = KEY_EMPTY;   // coalesced init
-        __syncthreads();
-        for (int j = beg + tid; j < end; j += RASTER_THREADS) {
-            const int id = a.tile_ids[j];
-            const float4 A = __ldg(&a.rec[2 * (int64_t)id]);
-            const float4 Bv = __ldg(&a.rec[2 * (int64_t)id + 1]);
-            if (!(A.z >= 0.0f)) continue;
-            const float cut = PER_POINT_CUTOFF ? __ldg(&a.cutoff[id]) : a.cutoff_uniform;
-            const unsigned long long key = make_key(A.z + 0.0f, id);
-            // conservative pixel-index range of the bbox (exact tests below), clipped to the tile
-            const float fx0 = (A.x - A.w + 1.0f) * half_S - 0.5f, fx1 = (A.x + A.w + 1.0f) * half_S - 0.5f;
-            const float fy0 = (A.y - Bv.x + 1.0f) * half_S - 0.5f, fy1 = (A.y + Bv.x + 1.0f) * half_S - 0.5f;
-            const int x0 = max(tx0, (int)fmaxf(ceilf(fx0) - 1.0f, -1.0f));
-            const int x1 = min(tx1, (int)fminf(floorf(fx1) + 1.0f, (float)S));
-            const int y0 = max(ty0, (int)fmaxf(ceilf(fy0) - 1.0f, -1.0f));
-            const int y1 = min(ty1, (int)fminf(floorf(fy1) + 1.0f, (float)S));
-            for (int yi = y0; yi <= y1; ++yi) {
-                const float dy = pix_to_ndc_fast(yi, S, inv_S, pow2) - A.y;
-                if (fabsf(dy) > Bv.x) continue;
-                unsigned long long *row = s_keys + ((yi - ty0) * RASTER_TILE - tx0) * KMAX;
-                for (int xi = x0; xi <= x1; ++xi) {
-                    unsigned long long *slot = row + xi * KMAX;
-                    if (key >= slot[KMAX - 1]) continue;             // cannot enter this pixel's list
-                    const float dx = pix_to_ndc_fast(xi, S, inv_S, pow2) - A.x;
-                    if (fabsf(dx) > A.w) continue;
-                    // rasterize_points.cu:94 -- same expression tree for q as the reference
-                    const float qv = Bv.y * dx * dx + Bv.z * dx * dy + Bv.w * dy * dy;
-                    if (qv > cut) continue;
-                    unsigned long long carry = key;
-#pragma unroll
-                    for (int k = 0; k < KMAX; ++k) {
-                        if (carry < slot[k]) {
-                            const unsigned long long old = atomicMin(&slot[k], carry);
-                            carry = old > carry ? old : carry;
-                        }
-                    }
-                }
-            }
-        }
-        __syncthreads();
-    }
-
-    // ---- epilogue: one thread per pixel ----
+    const int beg = 0, end = tile_has_entries ? 1 : 0;
+    // one thread per pixel
     const int xi = tx0 + (tid & (RASTER_TILE - 1));
     const int yi = ty0 + (tid >> 4);
     if (xi >= S || yi >= S) return;
@@ -340,6 +285,259 @@ raster_scatter_kernel(const __grid_constant__ RasterArgs a) {
     }
 }
 
+template <int KMAX, bool PER_POINT_CUTOFF, bool BLEND>
+__global__ void __launch_bounds__(RASTER_THREADS)
+raster_scatter_kernel(const __grid_constant__ RasterArgs a) {
+    __shared__ unsigned long long s_keys[RASTER_THREADS * KMAX];   // [pixel][k]
+
+    const int S = a.S, B = a.B, K = a.K;
+    const int n = blockIdx.y;
+    const int tile = blockIdx.x;
+    const int ty = tile / B, tx = tile - ty * B;
+    const int tid = threadIdx.x;
+    const int64_t tbase = ((int64_t)n * B * B + tile) * a.NS;
+    const int beg = a.tile_offsets[tbase], end = a.tile_offsets[tbase + a.NS];
+    const int tx0 = tx * RASTER_TILE, ty0 = ty * RASTER_TILE;
+    const int tx1 = min(tx0 + RASTER_TILE, S) - 1, ty1 = min(ty0 + RASTER_TILE, S) - 1;
+    const bool pow2 = (S & (S - 1)) == 0;
+    const float inv_S = 1.0f / (float)S, half_S = 0.5f * (float)S;
+
+    if (beg < end) {
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) s_keys[k * RASTER_THREADS + tid] = KEY_EMPTY;   // coalesced init
+        __syncthreads();
+        for (int j = beg + tid; j < end; j += RASTER_THREADS) {
+            const int id = a.tile_ids[j];
+            const float4 A = __ldg(&a.rec[2 * (int64_t)id]);
+            const float4 Bv = __ldg(&a.rec[2 * (int64_t)id + 1]);
+            if (!(A.z >= 0.0f)) continue;
+            const float cut = PER_POINT_CUTOFF ? __ldg(&a.cutoff[id]) : a.cutoff_uniform;
+            const unsigned long long key = make_key(A.z + 0.0f, id);
+            // conservative pixel-index range of the bbox (exact tests below), clipped to the tile
+            const float fx0 = (A.x - A.w + 1.0f) * half_S - 0.5f, fx1 = (A.x + A.w + 1.0f) * half_S - 0.5f;
+            const float fy0 = (A.y - Bv.x + 1.0f) * half_S - 0.5f, fy1 = (A.y + Bv.x + 1.0f) * half_S - 0.5f;
+            const int x0 = max(tx0, (int)fmaxf(ceilf(fx0) - 1.0f, -1.0f));
+            const int x1 = min(tx1, (int)fminf(floorf(fx1) + 1.0f, (float)S));
+            const int y0 = max(ty0, (int)fmaxf(ceilf(fy0) - 1.0f, -1.0f));
+            const int y1 = min(ty1, (int)fminf(floorf(fy1) + 1.0f, (float)S));
+            for (int yi = y0; yi <= y1; ++yi) {
+                const float dy = pix_to_ndc_fast(yi, S, inv_S, pow2) - A.y;
+                if (fabsf(dy) > Bv.x) continue;
+                unsigned long long *row = s_keys + ((yi - ty0) * RASTER_TILE - tx0) * KMAX;
+                for (int xi = x0; xi <= x1; ++xi) {
+                    unsigned long long *slot = row + xi * KMAX;
+                    if (key >= slot[KMAX - 1]) continue;             // cannot enter this pixel's list
+                    const float dx = pix_to_ndc_fast(xi, S, inv_S, pow2) - A.x;
+                    if (fabsf(dx) > A.w) continue;
+                    // rasterize_points.cu:94 -- same expression tree for q as the reference
+                    const float qv = Bv.y * dx * dx + Bv.z * dx * dy + Bv.w * dy * dy;
+                    if (qv > cut) continue;
+                    unsigned long long carry = key;
+#pragma unroll
+                    for (int k = 0; k < KMAX; ++k) {
+                        if (carry < slot[k]) {
+                            const unsigned long long old = atomicMin(&slot[k], carry);
+                            carry = old > carry ? old : carry;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    raster_epilogue<KMAX, BLEND>(a, s_keys, beg < end, n, tx0, ty0, pow2, inv_S);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Depth-sliced splat-parallel rasterizer (production path for K <= 8).
+//
+// Same shared-memory K-lists as raster_scatter_kernel, plus the three things that remove most of the
+// (splat, pixel) candidate tests on dense clouds:
+//   1. the tile's list arrives in NS front-to-back depth slices (binning key = tile x slice); before a slice
+//      is touched the kernel compares its lower depth bound with the largest K-th depth of the tile and
+//      stops if nothing behind that bound can enter any pixel's list;
+//   2. every entry is first tested against the K-th depths of the 4x4-pixel blocks its bbox touches (16
+//      values per tile, refreshed after every processing phase) -- one cheap, fully lane-parallel test;
+//   3. survivors are compacted into a shared-memory queue and rasterized in full batches, so the expensive
+//      per-pixel loops run with (nearly) all lanes busy instead of ~18 % (ncu, profiles/r01_ncu_v2_*).
+// ---------------------------------------------------------------------------------------------
+constexpr int RASTER_QCAP = 512;
+constexpr int RASTER_PCAP = 1024;
+
+// lock-free sorted insert of one key into a pixel's K slots (chain of atomicMin, see raster_scatter_kernel)
+template <int KMAX>
+__device__ __forceinline__ void klist_insert(unsigned long long *slot, unsigned long long carry) {
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+        if (carry < slot[k]) {
+            const unsigned long long old = atomicMin(&slot[k], carry);
+            carry = old > carry ? old : carry;
+        }
+    }
+}
+
+template <int KMAX, bool PER_POINT_CUTOFF, bool BLEND>
+__global__ void __launch_bounds__(RASTER_THREADS)
+raster_sliced_kernel(const __grid_constant__ RasterArgs a) {
+    __shared__ unsigned long long s_keys[RASTER_THREADS * KMAX];   // [pixel][k]
+    __shared__ int s_queue[RASTER_QCAP];
+    __shared__ unsigned long long s_pend_key[RASTER_PCAP];   // accepted fragments waiting for insertion
+    __shared__ unsigned short s_pend_pix[RASTER_PCAP];
+    __shared__ unsigned int s_blk[16];
+    __shared__ int s_qcount, s_npend;
+    __shared__ unsigned int s_tilemax;
+
+    const int S = a.S, B = a.B, K = a.K, NS = a.NS;
+    const int n = blockIdx.y;
+    const int tile = blockIdx.x;
+    const int ty = tile / B, tx = tile - ty * B;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int64_t tb = ((int64_t)n * B * B + tile) * NS;
+    const int beg = a.tile_offsets[tb], end = a.tile_offsets[tb + NS];
+    const int tx0 = tx * RASTER_TILE, ty0 = ty * RASTER_TILE;
+    const int tx1 = min(tx0 + RASTER_TILE, S) - 1, ty1 = min(ty0 + RASTER_TILE, S) - 1;
+    const bool pow2 = (S & (S - 1)) == 0;
+    const float inv_S = 1.0f / (float)S, half_S = 0.5f * (float)S;
+    constexpr unsigned FULL = 0xffffffffu;
+
+    unsigned int st_scanned = 0, st_surv = 0, st_tests = 0, st_acc = 0, st_skip = 0, st_visit = 0;
+    if (beg < end) {
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) s_keys[k * RASTER_THREADS + tid] = KEY_EMPTY;
+        if (tid < 16) s_blk[tid] = 0xffffffffu;
+        if (tid == 0) {
+            s_qcount = 0;
+            s_npend = 0;
+            s_tilemax = 0xffffffffu;
+        }
+        __syncthreads();
+        const SliceMap sm = make_slice_map(a.zrange, n, NS);
+        for (int s = 0; s < NS; ++s) {
+            const int sb = a.tile_offsets[tb + s], se = a.tile_offsets[tb + s + 1];
+            if (sb == se) continue;
+            // every entry of this and later slices has z >= slice_bound(s): stop if that cannot enter any list
+            if (s > 0 && __float_as_uint(slice_bound(sm, s)) > s_tilemax) {
+                if (tid == 0) st_skip += NS - s;
+                break;
+            }
+            if (tid == 0) st_visit++;
+            for (int base = sb; base < se; base += RASTER_THREADS) {
+                // ---- phase 1: entry-level cull against the block thresholds, survivors -> queue ----
+                const int j = base + tid;
+                bool survive = false;
+                int id = 0;
+                if (j < se) {
+                    st_scanned++;
+                    id = a.tile_ids[j];
+                    const float4 A = __ldg(&a.rec[2 * (int64_t)id]);
+                    const float ry = __ldg(&a.rec[2 * (int64_t)id + 1]).x;
+                    if (A.z >= 0.0f) {
+                        const int x0 = max(tx0, (int)fmaxf(ceilf((A.x - A.w + 1.0f) * half_S - 0.5f) - 1.0f, -1.0f));
+                        const int x1 = min(tx1, (int)fminf(floorf((A.x + A.w + 1.0f) * half_S - 0.5f) + 1.0f, (float)S));
+                        const int y0 = max(ty0, (int)fmaxf(ceilf((A.y - ry + 1.0f) * half_S - 0.5f) - 1.0f, -1.0f));
+                        const int y1 = min(ty1, (int)fminf(floorf((A.y + ry + 1.0f) * half_S - 0.5f) + 1.0f, (float)S));
+                        if (x0 <= x1 && y0 <= y1) {
+                            unsigned int zb = 0;
+                            for (int by = (y0 - ty0) >> 2; by <= (y1 - ty0) >> 2; ++by)
+                                for (int bx = (x0 - tx0) >> 2; bx <= (x1 - tx0) >> 2; ++bx) zb = max(zb, s_blk[by * 4 + bx]);
+                            survive = __float_as_uint(A.z + 0.0f) <= zb;
+                        }
+                    }
+                }
+                const unsigned m = __ballot_sync(FULL, survive);
+                int wbase = 0;
+                if (lane == 0 && m) wbase = atomicAdd(&s_qcount, __popc(m));
+                wbase = __shfl_sync(FULL, wbase, 0);
+                if (survive) {
+                    s_queue[wbase + __popc(m & ((1u << lane) - 1u))] = id;
+                    st_surv++;
+                }
+                __syncthreads();
+                const int nq = s_qcount;
+                __syncthreads();   // everyone has read nq before the next chunk's appends can change it
+                if (nq <= RASTER_QCAP - RASTER_THREADS && base + RASTER_THREADS < se) continue;   // keep filling
+                // ---- phase 2: rasterize the queued survivors, one splat per thread ----
+                for (int i = tid; i < nq; i += RASTER_THREADS) {
+                    const int sid = s_queue[i];
+                    const float4 A = __ldg(&a.rec[2 * (int64_t)sid]);
+                    const float4 Bv = __ldg(&a.rec[2 * (int64_t)sid + 1]);
+                    const float cut = PER_POINT_CUTOFF ? __ldg(&a.cutoff[sid]) : a.cutoff_uniform;
+                    const unsigned long long key = make_key(A.z + 0.0f, sid);
+                    const int x0 = max(tx0, (int)fmaxf(ceilf((A.x - A.w + 1.0f) * half_S - 0.5f) - 1.0f, -1.0f));
+                    const int x1 = min(tx1, (int)fminf(floorf((A.x + A.w + 1.0f) * half_S - 0.5f) + 1.0f, (float)S));
+                    const int y0 = max(ty0, (int)fmaxf(ceilf((A.y - Bv.x + 1.0f) * half_S - 0.5f) - 1.0f, -1.0f));
+                    const int y1 = min(ty1, (int)fminf(floorf((A.y + Bv.x + 1.0f) * half_S - 0.5f) + 1.0f, (float)S));
+                    for (int yi = y0; yi <= y1; ++yi) {
+                        const float dy = pix_to_ndc_fast(yi, S, inv_S, pow2) - A.y;
+                        if (fabsf(dy) > Bv.x) continue;
+                        unsigned long long *row = s_keys + ((yi - ty0) * RASTER_TILE - tx0) * KMAX;
+                        for (int xi = x0; xi <= x1; ++xi) {
+                            unsigned long long *slot = row + xi * KMAX;
+                            st_tests++;
+                            if (key >= slot[KMAX - 1]) continue;             // cannot enter this pixel's list
+                            const float dx = pix_to_ndc_fast(xi, S, inv_S, pow2) - A.x;
+                            if (fabsf(dx) > A.w) continue;
+                            // rasterize_points.cu:94 -- same expression tree for q as the reference
+                            const float qv = Bv.y * dx * dx + Bv.z * dx * dy + Bv.w * dy * dy;
+                            if (qv > cut) continue;
+                            st_acc++;
+                            // accepted and nearer than the pixel's K-th fragment: defer the (rare, long)
+                            // insertion so that it does not serialise the warp's test loop
+                            const int pi = atomicAdd(&s_npend, 1);
+                            if (pi < RASTER_PCAP) {
+                                s_pend_key[pi] = key;
+                                s_pend_pix[pi] = (unsigned short)((yi - ty0) * RASTER_TILE + (xi - tx0));
+                            } else {
+                                klist_insert<KMAX>(slot, key);
+                            }
+                        }
+                    }
+                }
+                __syncthreads();
+                {
+                    const int np = min(s_npend, RASTER_PCAP);
+                    for (int i = tid; i < np; i += RASTER_THREADS)
+                        klist_insert<KMAX>(s_keys + (int)s_pend_pix[i] * KMAX, s_pend_key[i]);
+                }
+                __syncthreads();
+                // ---- phase 3: refresh the block / tile thresholds (K-th depth, pixels outside the image never block) ----
+                if (tid < 16) s_blk[tid] = 0;
+                if (tid == 0) {
+                    s_qcount = 0;
+                    s_npend = 0;
+                }
+                __syncthreads();
+                {
+                    const int pxl = tid & (RASTER_TILE - 1), pyl = tid >> 4;
+                    const bool in_img = (tx0 + pxl < S) && (ty0 + pyl < S);
+                    const unsigned int kz = in_img ? (unsigned int)(s_keys[tid * KMAX + KMAX - 1] >> 32) : 0u;
+                    atomicMax(&s_blk[(pyl >> 2) * 4 + (pxl >> 2)], kz);
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    unsigned int mx = 0;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) mx = max(mx, s_blk[i]);
+                    s_tilemax = mx;
+                }
+                __syncthreads();
+            }
+        }
+    }
+    if (a.stats) {
+        atomicAdd(&a.stats[0], (unsigned long long)st_scanned);
+        atomicAdd(&a.stats[1], (unsigned long long)st_surv);
+        atomicAdd(&a.stats[2], (unsigned long long)st_tests);
+        atomicAdd(&a.stats[3], (unsigned long long)st_acc);
+        if (tid == 0) {
+            atomicAdd(&a.stats[4], (unsigned long long)st_skip);
+            atomicAdd(&a.stats[5], (unsigned long long)st_visit);
+        }
+    }
+    raster_epilogue<KMAX, BLEND>(a, s_keys, beg < end, n, tx0, ty0, pow2, inv_S);
+}
+
 template <int KMAX>
 static int launch_scatter(dss_ctx *ctx, const RasterArgs &a, cudaStream_t st) {
     dim3 grid((unsigned)(a.B * a.B), (unsigned)a.N);
@@ -347,14 +545,14 @@ static int launch_scatter(dss_ctx *ctx, const RasterArgs &a, cudaStream_t st) {
     const bool blend = a.image != nullptr;
     if (blend) {
         if (a.cutoff)
-            raster_scatter_kernel<KMAX, true, true><<<grid, RASTER_THREADS, 0, st>>>(a);
+            raster_sliced_kernel<KMAX, true, true><<<grid, RASTER_THREADS, 0, st>>>(a);
         else
-            raster_scatter_kernel<KMAX, false, true><<<grid, RASTER_THREADS, 0, st>>>(a);
+            raster_sliced_kernel<KMAX, false, true><<<grid, RASTER_THREADS, 0, st>>>(a);
     } else {
         if (a.cutoff)
-            raster_scatter_kernel<KMAX, true, false><<<grid, RASTER_THREADS, 0, st>>>(a);
+            raster_sliced_kernel<KMAX, true, false><<<grid, RASTER_THREADS, 0, st>>>(a);
         else
-            raster_scatter_kernel<KMAX, false, false><<<grid, RASTER_THREADS, 0, st>>>(a);
+            raster_sliced_kernel<KMAX, false, false><<<grid, RASTER_THREADS, 0, st>>>(a);
     }
     DSS_LAUNCH_CHECK(ctx);
     return DSS_OK;
@@ -396,16 +594,24 @@ int bin_and_raster(dss_ctx *ctx, RasterArgs a, const int64_t *first_idx, const i
                    int64_t P0, cudaStream_t st) {
     const int S = a.S;
     a.B = (S + RASTER_TILE - 1) / RASTER_TILE;
-    const int64_t nb = (int64_t)a.N * a.B * a.B;
+    a.NS = (a.K <= 8 && !a.force_pixel_parallel) ? choose_depth_slices(a.B) : 1;
+    const int64_t nb = (int64_t)a.N * a.B * a.B * a.NS;
     if (nb + 1 >= (int64_t)INT32_MAX) {
         set_error("too many tiles (%lld)", (long long)nb);
         return DSS_E_INVALID;
     }
     int32_t *counts = nullptr, *offsets = nullptr, *ids = nullptr;
+    float *zrange = nullptr;
     int rc;
     if ((rc = ctx_get(ctx, BUF_TILE_COUNTS, (size_t)(nb + 1), &counts))) return rc;
     if ((rc = ctx_get(ctx, BUF_TILE_OFFSETS, (size_t)(nb + 1), &offsets))) return rc;
-    if ((rc = bin_count_and_scan(ctx, a.rec, first_idx, num_points, a.N, P0, S, RASTER_TILE, counts, offsets, st)))
+    if (a.NS > 1) {
+        if ((rc = ctx_get(ctx, BUF_ZRANGE, (size_t)(2 * a.N), &zrange))) return rc;
+        if ((rc = compute_zrange(ctx, a.rec, first_idx, num_points, a.N, P0, zrange, st))) return rc;
+    }
+    a.zrange = zrange;
+    if ((rc = bin_count_and_scan(ctx, a.rec, first_idx, num_points, a.N, P0, S, RASTER_TILE, a.NS, zrange, counts,
+                                 offsets, st)))
         return rc;
     // the one host round-trip of the forward pass: size of the CSR id list
     DSS_CUDA_TRY(cudaMemcpyAsync(ctx->h_pinned, offsets + nb, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
@@ -417,16 +623,36 @@ int bin_and_raster(dss_ctx *ctx, RasterArgs a, const int64_t *first_idx, const i
     }
     if ((rc = ctx_get(ctx, BUF_TILE_IDS, (size_t)(total > 0 ? total : 1), &ids))) return rc;
     if (total > 0)
-        if ((rc = bin_scatter(ctx, a.rec, first_idx, num_points, a.N, P0, S, RASTER_TILE, offsets, counts, ids, st)))
+        if ((rc = bin_scatter(ctx, a.rec, first_idx, num_points, a.N, P0, S, RASTER_TILE, a.NS, zrange, offsets, counts,
+                              ids, st)))
             return rc;
     a.tile_offsets = offsets;
     a.tile_ids = ids;
+    a.stats = nullptr;
+    if (ctx->raster_stats) {
+        unsigned long long *sp = nullptr;
+        if ((rc = ctx_get(ctx, BUF_STATS, 8, &sp))) return rc;
+        a.stats = sp;
+    }
     return raster_forward(ctx, a, st);
 }
 
 }  // namespace dss
 
 extern "C" {
+
+int dss_debug_raster_stats(dss_ctx *ctx, int enable, uint64_t out[8]) {
+    using namespace dss;
+    DSS_REQUIRE(ctx != nullptr, "ctx is null");
+    unsigned long long *sp = nullptr;
+    int rc = ctx_get(ctx, BUF_STATS, 8, &sp);
+    if (rc) return rc;
+    DSS_CUDA_TRY(cudaDeviceSynchronize());
+    if (out) DSS_CUDA_TRY(cudaMemcpy(out, sp, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    if (enable) DSS_CUDA_TRY(cudaMemset(sp, 0, 8 * sizeof(unsigned long long)));
+    ctx->raster_stats = enable ? 1 : 0;
+    return DSS_OK;
+}
 
 int dss_splat_points(dss_ctx *ctx, const float *points, const float *ellipse_params, const float *cutoff_thres,
                      const float *radii, const int64_t *first_idx, const int64_t *num_points, int N, int64_t P,

@@ -65,6 +65,12 @@ DSS_API int dss_profile_num_stages(void);
 DSS_API const char *dss_profile_stage_name(int stage);
 DSS_API int dss_profile_read(dss_ctx *ctx, int stage, double *total_ms, int64_t *brackets);
 
+/* Debug work counters of the depth-sliced rasterizer (off by default; adds global atomics when on):
+ * out[0] tile-list entries scanned, [1] survivors of the block-threshold cull, [2] (splat,pixel) tests,
+ * [3] accepted fragments queued for insertion, [4] slices skipped by early termination, [5] slices visited.
+ * enable != 0 switches collection on (and zeroes the counters); out may be NULL. Synchronises the device. */
+DSS_API int dss_debug_raster_stats(dss_ctx *ctx, int enable, uint64_t out[8]);
+
 /* ---- exclusive prefix sum -----------------------------------------------------------------
  * Replaces prefix_sum.prefix_sum_cuda(grid_cnt, num_grids, grid_off)
  * (external/prefix_sum/prefix_sum.h:6-21, prefix_sum.cu:74-87,135-205): exclusive int32 scan of the
