@@ -342,8 +342,36 @@ occ_tile_kernel(const float4 *__restrict__ rec, const float *__restrict__ rs, co
         const int cy = min(max((int)floorf((py + 1.0f) * half_S), ty * OCC_TILE), ty * OCC_TILE + OCC_TILE - 1);
         const int ox = cx - Rw - wx0, oy = cy - Rw - wy0;
         float gx = 0.f, gy = 0.f;
-        for (int cb = 0; cb < Wwin; cb += lpp) {            // column blocks (one unless the window is > 32 wide)
-            const bool col_ok = have && (cb + gl < Wwin);
+        // windows wider than 32 columns: the first 32 columns go through the column-per-lane loop below, the
+        // remaining (Wwin - 32) x Wwin strip is walked in flattened order with all lanes busy (a second
+        // column block would run Wwin iterations with only Wwin - 32 lanes active)
+        const int Wmain = (lpp == 32 && Wwin > 32 && Wwin <= 64) ? 32 : Wwin;
+        if (Wmain < Wwin) {
+            const int Wt = Wwin - 32, total = Wt * Wwin;
+            int wy = lane / Wt, wx = lane - wy * Wt;
+            const int step_y = 32 / Wt, step_x = 32 - step_y * Wt;
+            for (int t = lane; t < total; t += 32) {
+                const int sx = ox + 32 + wx, sy = oy + wy;
+                const float g = s_g[sy * side + sx];
+                const float dx = s_xf[sx] - px, dy = s_yf[sy] - py;
+                const float d2 = fmaf(dy, dy, dx * dx);
+                const bool outside = (fabsf(dx) > rx) || (fabsf(dy) > ry);
+                const bool use = have && (g != 0.0f) && !(d2 > r2) && !(g > 0.0f && outside);
+                float inv;
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(fmaxf(d2, 1e-10f)));
+                const float w = use ? g * inv : 0.0f;
+                gx = fmaf(dx, w, gx);
+                gy = fmaf(dy, w, gy);
+                wx += step_x;
+                wy += step_y;
+                if (wx >= Wt) {
+                    wx -= Wt;
+                    wy += 1;
+                }
+            }
+        }
+        for (int cb = 0; cb < Wmain; cb += lpp) {           // column blocks (one unless the window is > 64 wide)
+            const bool col_ok = have && (cb + gl < Wmain);
             const int sx = col_ok ? ox + cb + gl : ox;      // inactive lanes read a valid column, result dropped
             const float dx = s_xf[sx] - px;
             const float dx2 = dx * dx;

@@ -362,8 +362,29 @@ raster_scatter_kernel(const __grid_constant__ RasterArgs a) {
 //   3. survivors are compacted into a shared-memory queue and rasterized in full batches, so the expensive
 //      per-pixel loops run with (nearly) all lanes busy instead of ~18 % (ncu, profiles/r01_ncu_v2_*).
 // ---------------------------------------------------------------------------------------------
+
+// Exact range of pixel indices i in [lo_clip, hi_clip] with |pix_to_ndc(i) - c| <= r, i.e. the pixels that
+// pass the reference's bbox test (rasterize_points.cu:92) for one axis: arithmetic estimate, then the
+// estimate is corrected by evaluating the very same fp32 test on the neighbouring pixels.
+__device__ __forceinline__ void pixel_range(float c, float r, int lo_clip, int hi_clip, int S, float inv_S, bool pow2,
+                                            float half_S, int &lo, int &hi) {
+    if (!(fabsf(c) < 4.0f) || !(r < 2.0f)) {   // far-away centre / huge splat: estimates lose accuracy, test every pixel
+        lo = lo_clip;
+        hi = hi_clip;
+        return;
+    }
+    lo = (int)fminf(fmaxf(ceilf((c - r + 1.0f) * half_S - 0.5f), -1.0f), (float)S);
+    hi = (int)fmaxf(fminf(floorf((c + r + 1.0f) * half_S - 0.5f), (float)S), -2.0f);
+    if (lo > 0 && !(fabsf(pix_to_ndc_fast(lo - 1, S, inv_S, pow2) - c) > r)) --lo;
+    else if (lo <= hi && lo < S && (fabsf(pix_to_ndc_fast(max(lo, 0), S, inv_S, pow2) - c) > r)) ++lo;
+    if (hi < S - 1 && !(fabsf(pix_to_ndc_fast(hi + 1, S, inv_S, pow2) - c) > r)) ++hi;
+    else if (hi >= lo && hi >= 0 && (fabsf(pix_to_ndc_fast(min(hi, S - 1), S, inv_S, pow2) - c) > r)) --hi;
+    lo = max(lo, lo_clip);
+    hi = min(hi, hi_clip);
+}
+
 constexpr int RASTER_QCAP = 512;
-constexpr int RASTER_PCAP = 1024;
+constexpr int RASTER_PCAP = 2048;
 
 // lock-free sorted insert of one key into a pixel's K slots (chain of atomicMin, see raster_scatter_kernel)
 template <int KMAX>
@@ -457,39 +478,58 @@ raster_sliced_kernel(const __grid_constant__ RasterArgs a) {
                 const int nq = s_qcount;
                 __syncthreads();   // everyone has read nq before the next chunk's appends can change it
                 if (nq <= RASTER_QCAP - RASTER_THREADS && base + RASTER_THREADS < se) continue;   // keep filling
-                // ---- phase 2: rasterize the queued survivors, one splat per thread ----
-                for (int i = tid; i < nq; i += RASTER_THREADS) {
-                    const int sid = s_queue[i];
-                    const float4 A = __ldg(&a.rec[2 * (int64_t)sid]);
-                    const float4 Bv = __ldg(&a.rec[2 * (int64_t)sid + 1]);
-                    const float cut = PER_POINT_CUTOFF ? __ldg(&a.cutoff[sid]) : a.cutoff_uniform;
+                // ---- phase 2: rasterize the queued survivors, one splat per thread.  Branch-free body inside
+                //      loops whose extents are warp-uniform (max over the warp's 32 splats): lanes whose own
+                //      bbox is smaller are predicated off instead of diverging; accepted fragments are pushed
+                //      with one warp-aggregated atomic per iteration ----
+                for (int ib = 0; ib < nq; ib += RASTER_THREADS) {
+                    const int i = ib + tid;
+                    const bool have = i < nq;
+                    const int sid = have ? s_queue[i] : 0;
+                    float4 A = make_float4(0.f, 0.f, 0.f, 0.f), Bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                    float cut = 0.f;
+                    if (have) {
+                        A = __ldg(&a.rec[2 * (int64_t)sid]);
+                        Bv = __ldg(&a.rec[2 * (int64_t)sid + 1]);
+                        cut = PER_POINT_CUTOFF ? __ldg(&a.cutoff[sid]) : a.cutoff_uniform;
+                    }
                     const unsigned long long key = make_key(A.z + 0.0f, sid);
-                    const int x0 = max(tx0, (int)fmaxf(ceilf((A.x - A.w + 1.0f) * half_S - 0.5f) - 1.0f, -1.0f));
-                    const int x1 = min(tx1, (int)fminf(floorf((A.x + A.w + 1.0f) * half_S - 0.5f) + 1.0f, (float)S));
-                    const int y0 = max(ty0, (int)fmaxf(ceilf((A.y - Bv.x + 1.0f) * half_S - 0.5f) - 1.0f, -1.0f));
-                    const int y1 = min(ty1, (int)fminf(floorf((A.y + Bv.x + 1.0f) * half_S - 0.5f) + 1.0f, (float)S));
-                    for (int yi = y0; yi <= y1; ++yi) {
+                    int x0 = tx0, x1 = tx0 - 1, y0 = ty0, y1 = ty0 - 1;
+                    if (have) {
+                        pixel_range(A.x, A.w, tx0, tx1, S, inv_S, pow2, half_S, x0, x1);
+                        pixel_range(A.y, Bv.x, ty0, ty1, S, inv_S, pow2, half_S, y0, y1);
+                    }
+                    const int w = max(x1 - x0 + 1, 0), h = max(y1 - y0 + 1, 0);
+                    const int Wm = __reduce_max_sync(FULL, w), Hm = __reduce_max_sync(FULL, h);
+                    for (int iy = 0; iy < Hm; ++iy) {
+                        const int yi = min(y0 + iy, ty1);
                         const float dy = pix_to_ndc_fast(yi, S, inv_S, pow2) - A.y;
-                        if (fabsf(dy) > Bv.x) continue;
-                        unsigned long long *row = s_keys + ((yi - ty0) * RASTER_TILE - tx0) * KMAX;
-                        for (int xi = x0; xi <= x1; ++xi) {
-                            unsigned long long *slot = row + xi * KMAX;
-                            st_tests++;
-                            if (key >= slot[KMAX - 1]) continue;             // cannot enter this pixel's list
+                        const bool row_ok = (iy < h) && !(fabsf(dy) > Bv.x);
+                        const unsigned long long *row = s_keys + ((yi - ty0) * RASTER_TILE - tx0) * KMAX;
+                        for (int ix = 0; ix < Wm; ++ix) {
+                            const int xi = min(x0 + ix, tx1);
+                            const unsigned long long kth = row[xi * KMAX + KMAX - 1];
                             const float dx = pix_to_ndc_fast(xi, S, inv_S, pow2) - A.x;
-                            if (fabsf(dx) > A.w) continue;
                             // rasterize_points.cu:94 -- same expression tree for q as the reference
                             const float qv = Bv.y * dx * dx + Bv.z * dx * dy + Bv.w * dy * dy;
-                            if (qv > cut) continue;
-                            st_acc++;
-                            // accepted and nearer than the pixel's K-th fragment: defer the (rare, long)
-                            // insertion so that it does not serialise the warp's test loop
-                            const int pi = atomicAdd(&s_npend, 1);
-                            if (pi < RASTER_PCAP) {
-                                s_pend_key[pi] = key;
-                                s_pend_pix[pi] = (unsigned short)((yi - ty0) * RASTER_TILE + (xi - tx0));
-                            } else {
-                                klist_insert<KMAX>(slot, key);
+                            const bool ok = row_ok && (ix < w) && (key < kth) && !(fabsf(dx) > A.w) && !(qv > cut);
+                            st_tests += (row_ok && ix < w) ? 1u : 0u;
+                            const unsigned pm = __ballot_sync(FULL, ok);
+                            if (pm) {
+                                int pbase = 0;
+                                if (lane == __ffs(pm) - 1) pbase = atomicAdd(&s_npend, __popc(pm));
+                                pbase = __shfl_sync(FULL, pbase, __ffs(pm) - 1);
+                                if (ok) {
+                                    st_acc++;
+                                    const int pi = pbase + __popc(pm & ((1u << lane) - 1u));
+                                    const int pixl = (yi - ty0) * RASTER_TILE + (xi - tx0);
+                                    if (pi < RASTER_PCAP) {
+                                        s_pend_key[pi] = key;
+                                        s_pend_pix[pi] = (unsigned short)pixl;
+                                    } else {
+                                        klist_insert<KMAX>(s_keys + pixl * KMAX, key);
+                                    }
+                                }
                             }
                         }
                     }

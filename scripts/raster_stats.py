@@ -18,3 +18,11 @@ print(st)
 print("visible points per view:", out.visible.view(V, P0).sum(1).tolist())
 print("occupied pixels per view:", (out.image[..., 3] > 0).view(V, -1).sum(1).tolist())
 print("per splat-view: scanned %.2f survivors %.2f tests %.2f accepted %.3f" % tuple(st[k] / (V * P0) for k in ("entries_scanned", "survivors", "pixel_tests", "accepted")))
+from dss_b200 import _C
+first = torch.arange(V, device=dev, dtype=torch.int64) * P0
+num = torch.full((V,), P0, device=dev, dtype=torch.int64)
+radii = out.records[:, 3:5].contiguous()
+rs = _C.search_radius(radii, out.visible, first, num, 5.0)
+print("search radius (px):", (rs * S / 2).tolist())
+vis = out.visible.bool()
+print("median radius of visible (px):", float(radii[vis].median() * S / 2), "mean", float(radii[vis].mean() * S / 2), "max", float(radii[vis].max() * S / 2))
