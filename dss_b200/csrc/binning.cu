@@ -127,6 +127,12 @@ __global__ void zrange_init_kernel(int32_t *zrange, int N) {
     }
 }
 
+int init_zrange(dss_ctx *ctx, float *zrange, int N, cudaStream_t st) {
+    zrange_init_kernel<<<(N + 127) / 128, 128, 0, st>>>(reinterpret_cast<int32_t *>(zrange), N);
+    DSS_LAUNCH_CHECK(ctx);
+    return DSS_OK;
+}
+
 int compute_zrange(dss_ctx *ctx, const float4 *rec, const int64_t *first_idx, const int64_t *num_points, int N,
                    int64_t P0, float *zrange, cudaStream_t st) {
     StageScope prof(ctx, ST_BIN_COUNT, st);
@@ -150,7 +156,7 @@ int compute_zrange(dss_ctx *ctx, const float4 *rec, const int64_t *first_idx, co
 // Fallback (plain global atomics) when the histogram of B*B tiles does not fit in shared memory.
 // ---------------------------------------------------------------------------------------------
 constexpr int BIN_THREADS = 256;
-constexpr int BIN_ITEMS = 8;
+constexpr int BIN_ITEMS = 16;
 constexpr int BIN_CHUNK = BIN_THREADS * BIN_ITEMS;
 constexpr int BIN_MAX_SMEM_TILES = 48 * 1024;   // 192 KB of histogram at most
 

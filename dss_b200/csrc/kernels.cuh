@@ -12,6 +12,7 @@ int pack_records(dss_ctx *ctx, const float *points, const float *radii, const fl
                  float4 *rec, cudaStream_t st);
 
 int choose_depth_slices(int B);
+int init_zrange(dss_ctx *ctx, float *zrange, int N, cudaStream_t st);
 int compute_zrange(dss_ctx *ctx, const float4 *rec, const int64_t *first_idx, const int64_t *num_points, int N,
                    int64_t P0, float *zrange, cudaStream_t st);
 

@@ -641,11 +641,11 @@ int bin_and_raster(dss_ctx *ctx, RasterArgs a, const int64_t *first_idx, const i
         return DSS_E_INVALID;
     }
     int32_t *counts = nullptr, *offsets = nullptr, *ids = nullptr;
-    float *zrange = nullptr;
+    float *zrange = const_cast<float *>(a.zrange);   // non-null: the caller's preprocess already produced it
     int rc;
     if ((rc = ctx_get(ctx, BUF_TILE_COUNTS, (size_t)(nb + 1), &counts))) return rc;
     if ((rc = ctx_get(ctx, BUF_TILE_OFFSETS, (size_t)(nb + 1), &offsets))) return rc;
-    if (a.NS > 1) {
+    if (a.NS > 1 && zrange == nullptr) {
         if ((rc = ctx_get(ctx, BUF_ZRANGE, (size_t)(2 * a.N), &zrange))) return rc;
         if ((rc = compute_zrange(ctx, a.rec, first_idx, num_points, a.N, P0, zrange, st))) return rc;
     }

@@ -23,6 +23,7 @@ struct PreArgs {
     float cutoffC, sigma, znear, zfar;
     float4 *rec;
     float *ndc, *ellipse, *radii, *scaler;
+    int32_t *zrange;   // (N,2) float bits: min / max view depth of the renderable splats, or null
 };
 
 // Python-side eps helpers of the reference (DSS/utils/mathHelper.py:10-22), zero counts as positive.
@@ -48,6 +49,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const __grid_constant__
     const ViewRange vr = view_range(a.shared_cloud ? nullptr : a.first_idx, a.num_points, n, a.P0);
     const float pix = 2.0f / (float)a.S;
     const float aa = a.sigma * pix * pix;
+    int zlo = 0x7f7fffff, zhi = 0;   // depth range of this thread's renderable splats (float bits)
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < vr.count;
          i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t s = vr.first + i;                     // packed slot
@@ -93,6 +95,11 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const __grid_constant__
             keep = keep && (nz < 0.0f);
         }
         if (!keep) zv = -1.0f;
+        if (zv >= 0.0f && zv < 3.0e38f) {
+            const int zb = __float_as_int(zv + 0.0f);
+            zlo = min(zlo, zb);
+            zhi = max(zhi, zb);
+        }
         const float xn = x / t, yn = y / t;
         a.rec[2 * s] = make_float4(xn, yn, zv, rx);
         a.rec[2 * s + 1] = make_float4(ry, ea, eb, ec);
@@ -112,6 +119,24 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const __grid_constant__
             a.radii[s * 2 + 1] = ry;
         }
     }
+    if (a.zrange) {   // one pair of atomics per block
+        __shared__ int s_lo[8], s_hi[8];
+        zlo = __reduce_min_sync(0xffffffffu, zlo);
+        zhi = __reduce_max_sync(0xffffffffu, zhi);
+        if ((threadIdx.x & 31) == 0) {
+            s_lo[threadIdx.x >> 5] = zlo;
+            s_hi[threadIdx.x >> 5] = zhi;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < 8; ++w) {
+                zlo = min(zlo, s_lo[w]);
+                zhi = max(zhi, s_hi[w]);
+            }
+            atomicMin(&a.zrange[2 * n], zlo);
+            atomicMax(&a.zrange[2 * n + 1], zhi);
+        }
+    }
 }
 
 static int check_common(const dss_render_args *g) {
@@ -127,7 +152,11 @@ static int check_common(const dss_render_args *g) {
     return DSS_OK;
 }
 
-static int run_preprocess(dss_ctx *ctx, const dss_render_args *g, float4 *rec, cudaStream_t st) {
+static int run_preprocess(dss_ctx *ctx, const dss_render_args *g, float4 *rec, cudaStream_t st, float *zrange = nullptr) {
+    if (zrange) {
+        int rc = init_zrange(ctx, zrange, g->n_views, st);
+        if (rc) return rc;
+    }
     if (g->P == 0 || g->P0 == 0) return DSS_OK;
     DSS_REQUIRE(g->points_world && g->normals_world && g->proj && g->view && g->h, "null input array");
     PreArgs a;
@@ -152,6 +181,7 @@ static int run_preprocess(dss_ctx *ctx, const dss_render_args *g, float4 *rec, c
     a.ellipse = g->ellipse;
     a.radii = g->radii;
     a.scaler = g->scaler;
+    a.zrange = reinterpret_cast<int32_t *>(zrange);
     dim3 grid(nblocks(g->P0, 256, ctx->sm_count, 8), g->n_views);
     StageScope prof(ctx, ST_PREPROCESS, st);
     preprocess_kernel<<<grid, 256, 0, st>>>(a);
@@ -293,7 +323,9 @@ int dss_render_forward(dss_ctx *ctx, const dss_render_args *g, void *stream) {
     float4 *rec = reinterpret_cast<float4 *>(g->records);
     if (!rec && (rc = ctx_get(ctx, BUF_RECORDS, (size_t)(2 * (g->P > 0 ? g->P : 1)), &rec))) return rc;
     DSS_REQUIRE((reinterpret_cast<uintptr_t>(rec) & 15) == 0, "records must be 16-byte aligned");
-    if ((rc = run_preprocess(ctx, g, rec, st))) return rc;
+    float *zrange = nullptr;
+    if ((rc = ctx_get(ctx, BUF_ZRANGE, (size_t)(2 * g->n_views), &zrange))) return rc;
+    if ((rc = run_preprocess(ctx, g, rec, st, zrange))) return rc;
     if (g->visible) DSS_CUDA_TRY(cudaMemsetAsync(g->visible, 0, (size_t)g->P, st));
     RasterArgs a;
     memset(&a, 0, sizeof(a));
@@ -313,6 +345,7 @@ int dss_render_forward(dss_ctx *ctx, const dss_render_args *g, void *stream) {
     a.image = g->image;
     a.weights = g->weights;
     a.visible = g->visible;
+    a.zrange = zrange;   // already filled by the preprocess kernel
     return bin_and_raster(ctx, a, g->shared_cloud ? nullptr : g->first_idx, g->num_points, g->P0, st);
 }
 
