@@ -204,7 +204,7 @@ __host__ __device__ __forceinline__ int occ_halo(float r, int S) { return (int)c
 __host__ __device__ __forceinline__ bool occ_tile_fits(float r, int S, int smem_bytes) {
     if (!(r >= 0.0f) || !(r < 4.0f) || smem_bytes <= 0) return false;
     const int side = OCC_TILE + 2 * occ_halo(r, S);
-    return (size_t)(side * side + 2 * side) * sizeof(float) <= (size_t)smem_bytes;
+    return (size_t)(2 * side * side + 2 * side) * sizeof(float) <= (size_t)smem_bytes;
 }
 
 __device__ __forceinline__ int centre_tile(float px, float py, int S, int OB) {
@@ -294,17 +294,23 @@ occ_tile_kernel(const float4 *__restrict__ rec, const float *__restrict__ rs, co
     const int ty = tile / OB, tx = tile - ty * OB;
     const int wx0 = tx * OCC_TILE - R, wy0 = ty * OCC_TILE - R;
     const float *gview = grad + ((int64_t)n * S * S) * pix_stride + pix_offset;
-    for (int i = threadIdx.x; i < side * side; i += OCC_TILE_THREADS) {
-        const int wy = i / side, wx = i - wy * side;
-        const int xi = wx0 + wx, yi = wy0 + wy;
-        float g = 0.0f;   // zero outside the image: such pixels then drop out of the sum by the g != 0 rule
-        if (xi >= 0 && xi < S && yi >= 0 && yi < S)
-            g = __ldg(gview + ((int64_t)(S - 1 - yi) * S + (S - 1 - xi)) * pix_stride);
-        s_g[i] = g;
+    float *s_gp = s_g + side * side, *s_xf = s_gp + side * side, *s_yf = s_xf + side;
+    for (int wy = threadIdx.x >> 5; wy < side; wy += OCC_TILE_THREADS / 32) {
+        const int yi = wy0 + wy;
+        const bool row_in = yi >= 0 && yi < S;
+        const float *grow = gview + ((int64_t)(S - 1 - yi) * S + (S - 1)) * pix_stride;
+        for (int wx = threadIdx.x & 31; wx < side; wx += 32) {
+            const int xi = wx0 + wx;
+            float g = 0.0f;   // zero outside the image: such pixels then drop out of the sums
+            if (row_in && xi >= 0 && xi < S) g = __ldg(grow - (int64_t)xi * pix_stride);
+            // Negative gradients act on the whole search disc, positive ones only inside the splat's own
+            // bounding box (rasterize_points_backward.cu:161-168): two planes, two loops, no per-pair sign tests.
+            s_g[wy * side + wx] = fminf(g, 0.0f);
+            s_gp[wy * side + wx] = fmaxf(g, 0.0f);
+        }
     }
     // exact pixel-centre NDC coordinates of the window's columns / rows (the reference's PixToNdc, division
     // included, evaluated once per CTA instead of once per pair)
-    float *s_xf = s_g + side * side, *s_yf = s_xf + side;
     for (int i = threadIdx.x; i < side; i += OCC_TILE_THREADS) {
         s_xf[i] = pix_to_ndc(wx0 + i, S);
         s_yf[i] = pix_to_ndc(wy0 + i, S);
@@ -325,17 +331,30 @@ occ_tile_kernel(const float4 *__restrict__ rec, const float *__restrict__ rs, co
     const int groups = 32 / lpp;
     const int grp = lane / lpp, gl = lane - grp * lpp;
     const int nwarps = OCC_TILE_THREADS / 32;
+    // software pipeline: the record of the next splat is fetched while the current one is being summed
+    int n_p = 0;
+    float4 n_A = make_float4(0.f, 0.f, 0.f, 0.f);
+    float n_ry = 0.f;
+    {
+        const int k = beg + warp * groups + grp;
+        if (k < end) {
+            n_p = tile_ids[k];
+            n_A = __ldg(&rec[2 * (int64_t)n_p]);
+            n_ry = __ldg(&rec[2 * (int64_t)n_p + 1]).x;
+        }
+    }
     for (int k0 = beg + warp * groups; k0 < end; k0 += nwarps * groups) {
         const int k = k0 + grp;
         const bool have = k < end;
-        const int p = have ? tile_ids[k] : 0;
-        float px = 0.f, py = 0.f, rx = 0.f, ry = 0.f;
-        if (have) {
-            const float4 A = __ldg(&rec[2 * (int64_t)p]);
-            px = A.x;
-            py = A.y;
-            rx = A.w;
-            ry = __ldg(&rec[2 * (int64_t)p + 1]).x;
+        const int p = n_p;
+        const float px = n_A.x, py = n_A.y, rx = n_A.w, ry = n_ry;
+        {
+            const int kn = k + nwarps * groups;
+            if (kn < end) {
+                n_p = tile_ids[kn];
+                n_A = __ldg(&rec[2 * (int64_t)n_p]);
+                n_ry = __ldg(&rec[2 * (int64_t)n_p + 1]).x;
+            }
         }
         // window origin in staged-window coordinates (always inside: the halo R = Rw + 1 covers it)
         const int cx = min(max((int)floorf((px + 1.0f) * half_S), tx * OCC_TILE), tx * OCC_TILE + OCC_TILE - 1);
@@ -355,11 +374,9 @@ occ_tile_kernel(const float4 *__restrict__ rec, const float *__restrict__ rs, co
                 const float g = s_g[sy * side + sx];
                 const float dx = s_xf[sx] - px, dy = s_yf[sy] - py;
                 const float d2 = fmaf(dy, dy, dx * dx);
-                const bool outside = (fabsf(dx) > rx) || (fabsf(dy) > ry);
-                const bool use = have && (g != 0.0f) && !(d2 > r2) && !(g > 0.0f && outside);
                 float inv;
                 asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(fmaxf(d2, 1e-10f)));
-                const float w = use ? g * inv : 0.0f;
+                const float w = (have && !(d2 > r2)) ? g * inv : 0.0f;
                 gx = fmaf(dx, w, gx);
                 gy = fmaf(dy, w, gy);
                 wx += step_x;
@@ -375,27 +392,44 @@ occ_tile_kernel(const float4 *__restrict__ rec, const float *__restrict__ rs, co
             const int sx = col_ok ? ox + cb + gl : ox;      // inactive lanes read a valid column, result dropped
             const float dx = s_xf[sx] - px;
             const float dx2 = dx * dx;
-            const bool out_x = fabsf(dx) > rx;
             const float *col = s_g + oy * side + sx;
             const float *yfp = s_yf + oy;
             float sw = 0.f, swy = 0.f;
 #pragma unroll 4
             for (int j = 0; j < Wwin; ++j) {
-                const float g = col[j * side];
+                const float g = col[j * side];                 // <= 0
                 const float dy = yfp[j] - py;
                 const float d2 = fmaf(dy, dy, dx2);
-                const bool outside = out_x || (fabsf(dy) > ry);
-                // rasterize_points_backward.cu:156-172
-                const bool use = (g != 0.0f) && !(d2 > r2) && !(g > 0.0f && outside);
                 float inv;
                 asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(fmaxf(d2, 1e-10f)));
-                const float w = use ? g * inv : 0.0f;
+                const float w = (d2 > r2) ? 0.0f : g * inv;    // rasterize_points_backward.cu:156, 170-172
                 sw += w;
                 swy = fmaf(w, dy, swy);
             }
             if (col_ok) {
                 gx = fmaf(dx, sw, gx);
                 gy += swy;
+            }
+        }
+        // positive gradients: only pixels inside the splat's bounding box (and the disc) count
+        {
+            const int bw = min(Rw, (int)fminf(ceilf(rx * half_S) + 1.0f, 4096.0f));
+            const int bh = min(Rw, (int)fminf(ceilf(ry * half_S) + 1.0f, 4096.0f));
+            const int Wb = 2 * bw + 1, total = have ? Wb * (2 * bh + 1) : 0;
+            const int bx0 = ox + Rw - bw, by0 = oy + Rw - bh;
+            const float inv_Wb = 1.0f / (float)Wb;
+            for (int t = gl; t < total; t += lpp) {
+                const int wy = __float2int_rz(((float)t + 0.5f) * inv_Wb), wx = t - wy * Wb;   // exact for these sizes
+                const int sx = bx0 + wx, sy = by0 + wy;
+                const float g = s_gp[sy * side + sx];         // >= 0
+                const float dx = s_xf[sx] - px, dy = s_yf[sy] - py;
+                const float d2 = fmaf(dy, dy, dx * dx);
+                const bool use = !(fabsf(dx) > rx) && !(fabsf(dy) > ry) && !(d2 > r2);
+                float inv;
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(fmaxf(d2, 1e-10f)));
+                const float w = use ? g * inv : 0.0f;
+                gx = fmaf(dx, w, gx);
+                gy = fmaf(dy, w, gy);
             }
         }
         for (int d = lpp >> 1; d > 0; d >>= 1) {
@@ -521,7 +555,7 @@ int occ_backward(dss_ctx *ctx, const float4 *rec, const uint8_t *visible, const 
     int smem = 64 * 1024;
     if (hint > 0.0f && hint < 4.0f) {
         const int side = OCC_TILE + 2 * (occ_halo(hint * 1.25f, S) + 1);
-        smem = (side * side + 2 * side) * (int)sizeof(float);
+        smem = (2 * side * side + 2 * side) * (int)sizeof(float);
         if (smem < 16 * 1024) smem = 16 * 1024;
         if (smem > 200 * 1024) smem = 200 * 1024;
     }

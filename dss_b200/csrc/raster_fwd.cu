@@ -182,7 +182,7 @@ raster_fwd_kernel(const __grid_constant__ RasterArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Splat-parallel ("scatter") rasterizer, the production path for K <= 8.
+// Splat-parallel ("scatter") rasterization: shared-memory K-lists (used by raster_sliced_kernel below).
 //
 // The pixel-parallel kernel above tests every splat that overlaps a warp's 8x4 patch in all 32 lanes,
 // although a ~5 px splat covers only ~1/5 of them.  Here the roles are swapped: the per-pixel K-nearest
@@ -285,74 +285,10 @@ __device__ __forceinline__ void raster_epilogue(const RasterArgs &a, const unsig
     }
 }
 
-template <int KMAX, bool PER_POINT_CUTOFF, bool BLEND>
-__global__ void __launch_bounds__(RASTER_THREADS)
-raster_scatter_kernel(const __grid_constant__ RasterArgs a) {
-    __shared__ unsigned long long s_keys[RASTER_THREADS * KMAX];   // [pixel][k]
-
-    const int S = a.S, B = a.B, K = a.K;
-    const int n = blockIdx.y;
-    const int tile = blockIdx.x;
-    const int ty = tile / B, tx = tile - ty * B;
-    const int tid = threadIdx.x;
-    const int64_t tbase = ((int64_t)n * B * B + tile) * a.NS;
-    const int beg = a.tile_offsets[tbase], end = a.tile_offsets[tbase + a.NS];
-    const int tx0 = tx * RASTER_TILE, ty0 = ty * RASTER_TILE;
-    const int tx1 = min(tx0 + RASTER_TILE, S) - 1, ty1 = min(ty0 + RASTER_TILE, S) - 1;
-    const bool pow2 = (S & (S - 1)) == 0;
-    const float inv_S = 1.0f / (float)S, half_S = 0.5f * (float)S;
-
-    if (beg < end) {
-#pragma unroll
-        for (int k = 0; k < KMAX; ++k) s_keys[k * RASTER_THREADS + tid] = KEY_EMPTY;   // coalesced init
-        __syncthreads();
-        for (int j = beg + tid; j < end; j += RASTER_THREADS) {
-            const int id = a.tile_ids[j];
-            const float4 A = __ldg(&a.rec[2 * (int64_t)id]);
-            const float4 Bv = __ldg(&a.rec[2 * (int64_t)id + 1]);
-            if (!(A.z >= 0.0f)) continue;
-            const float cut = PER_POINT_CUTOFF ? __ldg(&a.cutoff[id]) : a.cutoff_uniform;
-            const unsigned long long key = make_key(A.z + 0.0f, id);
-            // conservative pixel-index range of the bbox (exact tests below), clipped to the tile
-            const float fx0 = (A.x - A.w + 1.0f) * half_S - 0.5f, fx1 = (A.x + A.w + 1.0f) * half_S - 0.5f;
-            const float fy0 = (A.y - Bv.x + 1.0f) * half_S - 0.5f, fy1 = (A.y + Bv.x + 1.0f) * half_S - 0.5f;
-            const int x0 = max(tx0, (int)fmaxf(ceilf(fx0) - 1.0f, -1.0f));
-            const int x1 = min(tx1, (int)fminf(floorf(fx1) + 1.0f, (float)S));
-            const int y0 = max(ty0, (int)fmaxf(ceilf(fy0) - 1.0f, -1.0f));
-            const int y1 = min(ty1, (int)fminf(floorf(fy1) + 1.0f, (float)S));
-            for (int yi = y0; yi <= y1; ++yi) {
-                const float dy = pix_to_ndc_fast(yi, S, inv_S, pow2) - A.y;
-                if (fabsf(dy) > Bv.x) continue;
-                unsigned long long *row = s_keys + ((yi - ty0) * RASTER_TILE - tx0) * KMAX;
-                for (int xi = x0; xi <= x1; ++xi) {
-                    unsigned long long *slot = row + xi * KMAX;
-                    if (key >= slot[KMAX - 1]) continue;             // cannot enter this pixel's list
-                    const float dx = pix_to_ndc_fast(xi, S, inv_S, pow2) - A.x;
-                    if (fabsf(dx) > A.w) continue;
-                    // rasterize_points.cu:94 -- same expression tree for q as the reference
-                    const float qv = Bv.y * dx * dx + Bv.z * dx * dy + Bv.w * dy * dy;
-                    if (qv > cut) continue;
-                    unsigned long long carry = key;
-#pragma unroll
-                    for (int k = 0; k < KMAX; ++k) {
-                        if (carry < slot[k]) {
-                            const unsigned long long old = atomicMin(&slot[k], carry);
-                            carry = old > carry ? old : carry;
-                        }
-                    }
-                }
-            }
-        }
-        __syncthreads();
-    }
-
-    raster_epilogue<KMAX, BLEND>(a, s_keys, beg < end, n, tx0, ty0, pow2, inv_S);
-}
-
 // ---------------------------------------------------------------------------------------------
 // Depth-sliced splat-parallel rasterizer (production path for K <= 8).
 //
-// Same shared-memory K-lists as raster_scatter_kernel, plus the three things that remove most of the
+// Shared-memory K-lists as described above, plus the three things that remove most of the
 // (splat, pixel) candidate tests on dense clouds:
 //   1. the tile's list arrives in NS front-to-back depth slices (binning key = tile x slice); before a slice
 //      is touched the kernel compares its lower depth bound with the largest K-th depth of the tile and
@@ -386,7 +322,7 @@ __device__ __forceinline__ void pixel_range(float c, float r, int lo_clip, int h
 constexpr int RASTER_QCAP = 512;
 constexpr int RASTER_PCAP = 2048;
 
-// lock-free sorted insert of one key into a pixel's K slots (chain of atomicMin, see raster_scatter_kernel)
+// lock-free sorted insert of one key into a pixel's K slots (chain of atomicMin, see above)
 template <int KMAX>
 __device__ __forceinline__ void klist_insert(unsigned long long *slot, unsigned long long carry) {
 #pragma unroll
@@ -399,7 +335,7 @@ __device__ __forceinline__ void klist_insert(unsigned long long *slot, unsigned 
 }
 
 template <int KMAX, bool PER_POINT_CUTOFF, bool BLEND>
-__global__ void __launch_bounds__(RASTER_THREADS)
+__global__ void __launch_bounds__(RASTER_THREADS, 5)
 raster_sliced_kernel(const __grid_constant__ RasterArgs a) {
     __shared__ unsigned long long s_keys[RASTER_THREADS * KMAX];   // [pixel][k]
     __shared__ int s_queue[RASTER_QCAP];
