@@ -33,7 +33,7 @@ def algorithmic_bytes_per_view(P0, S, K):
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--points", type=int, default=1_000_000)
@@ -57,50 +57,87 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled during the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: NVML polled from a thread every ~2 ms
+    (nvidia-smi -lms cannot deliver a sample inside a region of a few tens of ms); nvidia-smi is the fallback."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.lines, self.proc = index, [], None
+        self.index, self.sm, self.bits, self.mx, self.source = index, [], 0, None, None
+        self._stop = threading.Event()
+        self.t = None
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [x.strip() for x in vis.split(",") if x.strip()]
+            if self.index < len(ids) and ids[self.index].isdigit():
+                return int(ids[self.index])
+        return self.index
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.source = "nvml"
+            self.t = threading.Thread(target=self._poll_nvml, daemon=True)
         except Exception:
-            self.proc = None
+            self.source = "nvidia-smi"
+            self.t = threading.Thread(target=self._poll_smi, daemon=True)
+        self.t.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _poll_nvml(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def _poll_smi(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        self.smi_reasons = set()
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self._physical_index()), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                self.sm.append(float(f[0]))
+                self.mx = float(f[1])
+                for nm, v in zip(names, f[3:7]):
+                    if v.lower().startswith("active"):
+                        self.smi_reasons.add(nm)
+            except Exception:
+                time.sleep(0.05)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.12)
-        self.proc.terminate()
-        sm, mx, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0]))
-                mx = float(f[1])
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
+        self._stop.set()
+        if self.t is not None:
+            self.t.join(timeout=6)
+        reasons = set()
+        if self.source == "nvml":
+            nv = self.nv
+            for nm, bit in (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown),
+                            ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                            ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown),
+                            ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap),
+                            ("hw_power_brake", nv.nvmlClocksEventReasonHwPowerBrakeSlowdown)):
+                if self.bits & bit:
                     reasons.add(nm)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        else:
+            reasons = getattr(self, "smi_reasons", set())
+        sm = sorted(self.sm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.mx, "reasons": ["no clock samples"], "samples": 0,
+                    "source": self.source}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": self.mx, "reasons": sorted(reasons),
+                "samples": len(sm), "source": self.source}
 
 
 # ------------------------------------------------------------------------------------------------

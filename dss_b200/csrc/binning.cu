@@ -305,7 +305,7 @@ int bin_count_and_scan(dss_ctx *ctx, const float4 *rec, const int64_t *first_idx
     if (P0 > 0) {
         dim3 grid((unsigned)((P0 + BIN_CHUNK - 1) / BIN_CHUNK), N);
         StageScope prof(ctx, ST_BIN_COUNT, st);
-        if ((int64_t)B * B * NS <= BIN_MAX_SMEM_TILES && B < 32768) {
+        if ((int64_t)B * B * NS <= BIN_MAX_SMEM_TILES && B < 32768 && !ctx->bin_direct) {
             const size_t smem = (size_t)B * B * NS * sizeof(int32_t);
             int rc = prepare_smem(bin_count_kernel<true>, smem);
             if (rc) return rc;
@@ -327,7 +327,7 @@ int bin_scatter(dss_ctx *ctx, const float4 *rec, const int64_t *first_idx, const
     if (P0 > 0) {
         dim3 grid((unsigned)((P0 + BIN_CHUNK - 1) / BIN_CHUNK), N);
         StageScope prof(ctx, ST_BIN_SCATTER, st);
-        if ((int64_t)B * B * NS <= BIN_MAX_SMEM_TILES && B < 32768) {
+        if ((int64_t)B * B * NS <= BIN_MAX_SMEM_TILES && B < 32768 && !ctx->bin_direct) {
             const size_t smem = (size_t)B * B * NS * sizeof(int32_t);
             int rc = prepare_smem(bin_scatter_kernel<true>, smem);
             if (rc) return rc;

@@ -55,6 +55,8 @@ enum BufId {
     BUF_CUTOFF,
     BUF_ZRANGE,
     BUF_STATS,
+    BUF_OCC_REC,      // compact tile-ordered {px,py,rx,ry} of the visible splats (occupancy backward)
+    BUF_OCC_PLANES,   // zero-padded g-/g+ planes of the alpha gradient
     NUM_BUFS
 };
 
@@ -63,7 +65,7 @@ enum BufId {
 namespace dss {
 enum Stage {
     ST_PACK = 0, ST_PREPROCESS, ST_BIN_COUNT, ST_SCAN, ST_BIN_SCATTER, ST_RASTER_FWD, ST_VISIBILITY,
-    ST_SEARCH_RADIUS, ST_OCC_BWD, ST_COLOUR_BWD, ST_ZBUF_BWD, ST_CHAIN, ST_GRID, NUM_STAGES
+    ST_SEARCH_RADIUS, ST_OCC_BWD, ST_COLOUR_BWD, ST_ZBUF_BWD, ST_CHAIN, ST_GRID, ST_OCC_BIN, NUM_STAGES
 };
 struct ProfPending {
     cudaEvent_t a, b;
@@ -85,6 +87,7 @@ struct dss_ctx {
     int n_pending, cap_pending;
     int open[8], n_open;
     int raster_stats;   // debug: accumulate raster work counters
+    int bin_direct;     // tuning (env DSS_BIN_DIRECT): tile binning with plain global atomics instead of per-block histograms
     double stage_ms[dss::NUM_STAGES];
     int64_t stage_calls[dss::NUM_STAGES];
 };

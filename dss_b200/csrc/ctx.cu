@@ -101,7 +101,7 @@ static void prof_collect(dss_ctx *ctx) {
 
 static const char *k_stage_names[NUM_STAGES] = {
     "pack_records", "preprocess", "bin_count", "scan", "bin_scatter", "raster_forward", "visibility",
-    "search_radius", "occ_backward", "colour_backward", "zbuf_backward", "chain_world", "grid_2d"};
+    "search_radius", "occ_backward", "colour_backward", "zbuf_backward", "chain_world", "grid_2d", "occ_bin"};
 
 // ---------------------------------------------------------------------------------------------
 // Exclusive scan, single pass with decoupled look-back.  Replaces external/prefix_sum
@@ -263,6 +263,10 @@ int dss_create(dss_ctx **out) {
     memset(c, 0, sizeof(*c));
     c->device = dev;
     c->sm_count = prop.multiProcessorCount;
+    {
+        const char *e = getenv("DSS_BIN_DIRECT");
+        c->bin_direct = (e && e[0] == '1') ? 1 : 0;
+    }
     if (cudaMallocHost((void **)&c->h_pinned, 64 * sizeof(int64_t)) != cudaSuccess) {
         cudaGetLastError();
         delete c;

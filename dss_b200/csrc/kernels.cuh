@@ -92,7 +92,8 @@ int visibility_from_idx(dss_ctx *ctx, const int32_t *idx, int64_t num_pixels, in
 int search_radius(dss_ctx *ctx, const float4 *rec, const float *radii, const uint8_t *visible,
                   const int64_t *first_idx, const int64_t *num_points, int N, int64_t P0, float radii_s,
                   float *rs, cudaStream_t st);
-int occ_backward(dss_ctx *ctx, const float4 *rec, const uint8_t *visible, const float *rs,
+// rs is an input when radii_s < 0, otherwise rs[n] = radii_s * lower median of the visible radii is computed here
+int occ_backward(dss_ctx *ctx, const float4 *rec, const uint8_t *visible, float *rs, float radii_s,
                  const float *grad_occ, int pix_stride, int pix_offset, const int64_t *first_idx,
                  const int64_t *num_points, int N, int64_t P0, int S, float *grad_xy, cudaStream_t st);
 int zbuf_backward(dss_ctx *ctx, const int32_t *idx, const float *grad_zbuf, int64_t num_pixels, int K,

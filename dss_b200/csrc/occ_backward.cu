@@ -1,0 +1,784 @@
+// occ_backward.cu -- occupancy ("fast") backward: point <- pixel gather over tile-sorted compact records.
+//
+// Replaces the fast branch of EllipticalRasterizer.backward (DSS/core/rasterizer.py:845-972) and
+// RasterizePointsBackwardCudaFastKernel (DSS/csrc/rasterize_points_backward.cu:30-212).  The reference
+// scatters pixel -> point with two float atomics per (pixel, point) pair after building an FRNN grid with
+// per-view host loops.  Here (all on the device, no host round trip, no atomics, deterministic):
+//
+//   occ_planes   alpha gradient -> two zero-padded planes per view in NDC-index orientation: g- = min(g, 0)
+//                (acts on the whole search disc) and g+ = max(g, 0) (acts inside the splat's bbox only,
+//                rasterize_points_backward.cu:161-168)
+//   occ_bin x2   visible splats -> 32x32-pixel tiles by centre (count / scan / scatter); the scatter writes
+//                COMPACT tile-ordered records {px, py, rx, ry} + ids, so everything downstream reads
+//                contiguous memory
+//   select x4    exact lower median of the visible radii per view (radix select) over the compact records
+//                (rasterizer.py:888) -> search radius r_n
+//   occ_tile     one CTA per (tile, chunk of its list): the (32 + 2R)^2 windows of both planes and the
+//                chunk's records are staged in shared memory by the TMA engine (cp.async.bulk, one row per
+//                copy, completion on an mbarrier); lanes own PAIRS of window columns and walk the rows with
+//                packed f32x2 arithmetic (fma.rn.f32x2 / add / mul: two pairs per instruction slot), the
+//                x half of the sum is factored (sum_rows dx*w = dx * sum_rows w).
+#include <math_constants.h>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace dss {
+
+constexpr int OCC_TILE = 32;            // pixels per side of a backward tile
+constexpr int OCC_THREADS = 256;
+constexpr int OCC_RCAP = 128;           // records staged per TMA chunk
+constexpr int OCC_SLACK = 64;           // floats of slack behind each staged plane / the column table
+constexpr int OCC_MIN_PART = 64;        // a tile's list is split over CTAs of at least this many splats
+constexpr int OCC_MAX_PARTS = 32;
+constexpr int OCC_RBOX_MAX = 60;        // largest window halo the tile kernel stages (2 planes <= ~190 KB)
+
+// Window halo (pixels) that covers the search disc of radius r (NDC) around any point of a tile, plus slack for
+// the rounding of floor() when the centre pixel is located.
+__host__ __device__ __forceinline__ int occ_halo(float r, int S) { return (int)ceilf(r * 0.5f * (float)S) + 2; }
+// Is view n handled by the tile kernel (window fits the staged box)?  Evaluated identically by both kernels.
+__host__ __device__ __forceinline__ bool occ_fits(float r, int S, int R_box) {
+    if (!(r >= 0.0f) || !(r < 4.0f) || R_box <= 0) return false;
+    return occ_halo(r, S) <= R_box;
+}
+
+__device__ __forceinline__ int centre_pixel(float p, int S) {
+    return min(max((int)floorf((p + 1.0f) * (0.5f * (float)S)), 0), S - 1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// planes: (N, 2, Hp, W) floats, plane 0 = min(g, 0), plane 1 = max(g, 0); element (y, x) holds NDC-index pixel
+// (yi, xi) = (y - PAD, x - PAD), i.e. image row S-1-yi, col S-1-xi (rasterize_points_backward.cu:100-104);
+// zero outside the image so that border windows need no bounds tests.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+occ_planes_kernel(const float *__restrict__ grad, int pix_stride, int pix_offset, int S, int PAD, int W, int Hp,
+                  float *__restrict__ planes) {
+    const int n = blockIdx.z, y = blockIdx.y;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= W) return;
+    const int yi = y - PAD, xi = x - PAD;
+    float g = 0.0f;
+    if (yi >= 0 && yi < S && xi >= 0 && xi < S)
+        g = __ldg(grad + (((int64_t)n * S + (S - 1 - yi)) * S + (S - 1 - xi)) * pix_stride + pix_offset);
+    float *p = planes + (((int64_t)n * 2) * Hp + y) * W + x;
+    p[0] = fminf(g, 0.0f);
+    p[(int64_t)Hp * W] = fmaxf(g, 0.0f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Bin the visible splats by the tile that contains their (clamped) centre: one entry per splat, so the
+// lists are bounded by P and no host round trip is needed.  PASS 0 counts, PASS 1 scatters compact records.
+// ---------------------------------------------------------------------------------------------
+template <int PASS>
+__global__ void __launch_bounds__(256)
+occ_bin_kernel(const float4 *__restrict__ rec, const uint8_t *__restrict__ visible,
+               const int64_t *__restrict__ first_idx, const int64_t *__restrict__ num_points, int64_t P0_shared,
+               int S, int OB, int32_t *__restrict__ counters, float4 *__restrict__ crec, int32_t *__restrict__ cids) {
+    extern __shared__ int32_t s_hist[];
+    const int n = blockIdx.y;
+    const int nt = OB * OB;
+    const ViewRange vr = view_range(first_idx, num_points, n, P0_shared);
+    constexpr int ITEMS = 8;
+    const int64_t chunk0 = (int64_t)blockIdx.x * (256 * ITEMS);
+    if (chunk0 >= vr.count) return;
+    for (int t = threadIdx.x; t < nt; t += 256) s_hist[t] = 0;
+    __syncthreads();
+    int tile[ITEMS];
+    float4 cr[ITEMS];
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+        tile[j] = -1;
+        const int64_t i = chunk0 + j * 256 + threadIdx.x;
+        if (i < vr.count && visible[vr.first + i]) {
+            const float4 A = __ldg(&rec[2 * (vr.first + i)]);
+            const float ry = __ldg(&rec[2 * (vr.first + i) + 1]).x;
+            cr[j] = make_float4(A.x, A.y, A.w, ry);
+            tile[j] = (centre_pixel(A.y, S) / OCC_TILE) * OB + centre_pixel(A.x, S) / OCC_TILE;
+            atomicAdd(&s_hist[tile[j]], 1);
+        }
+    }
+    __syncthreads();
+    int32_t *cnt = counters + (int64_t)n * nt;
+    for (int t = threadIdx.x; t < nt; t += 256) {
+        const int v = s_hist[t];
+        if (v) {
+            const int base = atomicAdd(&cnt[t], v);
+            if (PASS == 1) s_hist[t] = base;
+        }
+    }
+    if (PASS == 0) return;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j)
+        if (tile[j] >= 0) {
+            const int slot = atomicAdd(&s_hist[tile[j]], 1);
+            crec[slot] = cr[j];
+            cids[slot] = (int32_t)(vr.first + chunk0 + j * 256 + threadIdx.x);
+        }
+}
+
+static inline unsigned int occ_nblocks(int64_t items, int threads, int sm_count, int per_sm) {
+    int64_t b = (items + threads - 1) / threads;
+    const int64_t cap = (int64_t)sm_count * per_sm;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (unsigned int)b;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Search radius: radii_s * lower median of the flattened (rx, ry) of the view's visible points
+// (rasterizer.py:888, torch.median = element (m-1)/2 of the ascending sort of m = 2 n_vis values).
+// Exact 4-pass (8 bits each, MSB first) radix select on the order-preserving uint image of the floats.
+// hist layout: (N, 4, 256) uint32.  Each block first re-derives the prefix chosen by the previous
+// passes from their (complete) histograms -- 256-bin scans, negligible -- so no host involvement.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int float_key(float f) {
+    const unsigned int b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key_float(unsigned int k) {
+    const unsigned int b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+    return __uint_as_float(b);
+}
+
+// Walk histograms of passes [0, upto) and return (prefix, remaining rank).  Executed by one warp.
+__device__ void select_resolve(const unsigned int *hist_n, int upto, unsigned int &prefix,
+                               unsigned long long &rank, unsigned long long &total) {
+    const int lane = threadIdx.x & 31;
+    prefix = 0;
+    rank = 0;
+    total = 0;
+    for (int pass = 0; pass < upto; ++pass) {
+        const unsigned int *h = hist_n + pass * 256;
+        // each lane owns 8 consecutive bins
+        unsigned int c[8];
+        unsigned long long s = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            c[j] = h[lane * 8 + j];
+            s += c[j];
+        }
+        unsigned long long incl = s;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        const unsigned long long tot = __shfl_sync(0xffffffffu, incl, 31);
+        if (pass == 0) {
+            total = tot;
+            rank = (tot > 0) ? (tot - 1) / 2 : 0;  // lower median
+        }
+        unsigned long long excl = incl - s;
+        // find the bin containing `rank`
+        int found = -1;
+        unsigned long long found_excl = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (found < 0 && rank >= excl && rank < excl + c[j]) {
+                found = lane * 8 + j;
+                found_excl = excl;
+            }
+            excl += c[j];
+        }
+        const unsigned int who = __ballot_sync(0xffffffffu, found >= 0);
+        int digit = 0;
+        unsigned long long dexcl = 0;
+        if (who) {
+            const int src = __ffs(who) - 1;
+            digit = __shfl_sync(0xffffffffu, found, src);
+            dexcl = __shfl_sync(0xffffffffu, found_excl, src);
+        }
+        prefix = (prefix << 8) | (unsigned int)digit;
+        rank -= dexcl;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+select_hist_kernel(const float4 *__restrict__ rec, const float *__restrict__ radii,
+                   const uint8_t *__restrict__ visible, const int64_t *__restrict__ first_idx,
+                   const int64_t *__restrict__ num_points, int64_t P0_shared, int pass,
+                   unsigned int *__restrict__ hist) {
+    __shared__ unsigned int s_hist[256];
+    __shared__ unsigned int s_prefix;
+    const int n = blockIdx.y;
+    unsigned int *hist_n = hist + (int64_t)n * 4 * 256;
+    s_hist[threadIdx.x] = 0;
+    if (threadIdx.x < 32) {
+        unsigned int prefix;
+        unsigned long long rank, total;
+        select_resolve(hist_n, pass, prefix, rank, total);
+        if (threadIdx.x == 0) s_prefix = prefix;
+    }
+    __syncthreads();
+    const unsigned int prefix = s_prefix;
+    const int shift = 24 - 8 * pass;
+    const ViewRange vr = view_range(first_idx, num_points, n, P0_shared);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < vr.count;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = vr.first + i;
+        if (!visible[p]) continue;
+        float rx, ry;
+        if (rec) {
+            rx = __ldg(&rec[2 * p]).w;
+            ry = __ldg(&rec[2 * p + 1]).x;
+        } else {
+            rx = radii[p * 2];
+            ry = radii[p * 2 + 1];
+        }
+        const unsigned int kx = float_key(rx), ky = float_key(ry);
+        if (pass == 0 || (kx >> (shift + 8)) == prefix) atomicAdd(&s_hist[(kx >> shift) & 255u], 1u);
+        if (pass == 0 || (ky >> (shift + 8)) == prefix) atomicAdd(&s_hist[(ky >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    const unsigned int v = s_hist[threadIdx.x];
+    if (v) atomicAdd(&hist_n[pass * 256 + threadIdx.x], v);
+}
+
+__global__ void select_final_kernel(const unsigned int *__restrict__ hist, float radii_s, float *__restrict__ rs) {
+    const int n = blockIdx.x;
+    unsigned int prefix;
+    unsigned long long rank, total;
+    select_resolve(hist + (int64_t)n * 4 * 256, 4, prefix, rank, total);
+    if (threadIdx.x == 0) rs[n] = (total > 0) ? key_float(prefix) * radii_s : 0.0f;
+}
+
+int search_radius(dss_ctx *ctx, const float4 *rec, const float *radii, const uint8_t *visible,
+                  const int64_t *first_idx, const int64_t *num_points, int N, int64_t P0, float radii_s,
+                  float *rs, cudaStream_t st) {
+    if (N <= 0) return DSS_OK;
+    unsigned int *hist = nullptr;
+    int rc = ctx_get(ctx, BUF_SELECT, (size_t)N * 4 * 256, &hist);
+    if (rc) return rc;
+    StageScope prof(ctx, ST_SEARCH_RADIUS, st);
+    DSS_CUDA_TRY(cudaMemsetAsync(hist, 0, (size_t)N * 4 * 256 * sizeof(unsigned int), st));
+    if (P0 > 0) {
+        dim3 grid(occ_nblocks(P0, 256, ctx->sm_count, 4), N);
+        for (int pass = 0; pass < 4; ++pass) {
+            select_hist_kernel<<<grid, 256, 0, st>>>(rec, radii, visible, first_idx, num_points, P0, pass, hist);
+            DSS_LAUNCH_CHECK(ctx);
+        }
+    }
+    select_final_kernel<<<N, 32, 0, st>>>(hist, radii_s, rs);
+    DSS_LAUNCH_CHECK(ctx);
+    return DSS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Search radius: radii_s * lower median of the flattened (rx, ry) of the view's visible points
+// (rasterizer.py:888; torch.median = element (m-1)/2 of the ascending sort of m = 2 n_vis values).
+// Exact 4-pass radix select (8 bits per pass, MSB first) over the compact records of the view, which are
+// contiguous: [tile_offsets[n*nt], tile_offsets[(n+1)*nt]).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+select_hist_compact_kernel(const float4 *__restrict__ crec, const int32_t *__restrict__ tile_offsets, int nt, int pass,
+                           unsigned int *__restrict__ hist) {
+    __shared__ unsigned int s_hist[256];
+    __shared__ unsigned int s_prefix;
+    const int n = blockIdx.y;
+    unsigned int *hist_n = hist + (int64_t)n * 4 * 256;
+    s_hist[threadIdx.x] = 0;
+    if (threadIdx.x < 32) {
+        unsigned int prefix;
+        unsigned long long rank, total;
+        select_resolve(hist_n, pass, prefix, rank, total);
+        if (threadIdx.x == 0) s_prefix = prefix;
+    }
+    __syncthreads();
+    const unsigned int prefix = s_prefix;
+    const int shift = 24 - 8 * pass;
+    const int beg = tile_offsets[(int64_t)n * nt], end = tile_offsets[(int64_t)(n + 1) * nt];
+    for (int i = beg + blockIdx.x * blockDim.x + threadIdx.x; i < end; i += gridDim.x * blockDim.x) {
+        const float4 c = __ldg(&crec[i]);
+        const unsigned int kx = float_key(c.z), ky = float_key(c.w);
+        if (pass == 0 || (kx >> (shift + 8)) == prefix) atomicAdd(&s_hist[(kx >> shift) & 255u], 1u);
+        if (pass == 0 || (ky >> (shift + 8)) == prefix) atomicAdd(&s_hist[(ky >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    const unsigned int v = s_hist[threadIdx.x];
+    if (v) atomicAdd(&hist_n[pass * 256 + threadIdx.x], v);
+}
+
+// ---------------------------------------------------------------------------------------------
+// TMA (bulk async copy) + mbarrier helpers: raw PTX, sm_90+ encoding, issued by single threads.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// bounded wait: a lost transaction traps (surfaces as a launch error) instead of hanging the device
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    unsigned int spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 24)) __trap();
+    }
+}
+
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+struct OccTileArgs {
+    const float4 *crec;          // compact tile-ordered records {px, py, rx, ry}
+    const int32_t *cids;         // packed splat id of every compact record
+    const int32_t *tile_offsets; // (N*OB*OB + 1)
+    const float *rs;             // (N,) search radius
+    const float *planes;         // (N, 2, Hp, W)
+    float2 *grad_xy;             // (P,) out
+    int S, OB, R_box, side, W, Hp;
+};
+
+// Row walk of one column pair.  `off` = float index of (row j0, column sx) in the staged planes; yf2 holds the NDC y
+// of row j0 - 1 (POW2: advanced by exact additions of the pixel pitch, which are exact when S is a power of two --
+// every value is a multiple of 1/S below 2^24/S; otherwise the exact table s_yf is read).
+// CENTRE = rows that may contain the pixel under the point (d2 -> 0: clamp like the reference's eps_denom, 1e-10)
+// and the rows the splat's own bounding box can reach (positive gradients count there).
+template <bool CENTRE, bool POW2>
+__device__ __forceinline__ void occ_rows(int j0, int j1, const float *__restrict__ s_gm, const float *__restrict__ s_gp,
+                                         const float *__restrict__ s_yf_row0, int side, int off, float2 &yf2,
+                                         const float2 pix2, const float2 npy2, const float2 dxsq, const float ry,
+                                         const bool colin0, const bool colin1, const float r2, float2 &sw,
+                                         float2 &swy) {
+#pragma unroll 2
+    for (int j = j0; j < j1; ++j) {
+        float2 g = *reinterpret_cast<const float2 *>(s_gm + off);
+        if (POW2) {
+            yf2 = __fadd2_rn(yf2, pix2);
+        } else {
+            const float yf = s_yf_row0[j];
+            yf2 = make_float2(yf, yf);
+        }
+        const float2 dy2 = __fadd2_rn(yf2, npy2);
+        const float2 d2 = __ffma2_rn(dy2, dy2, dxsq);          // dy*dy + dx*dx, two columns at once
+        const bool out0 = d2.x > r2, out1 = d2.y > r2;         // rasterize_points_backward.cu:156
+        float2 inv;
+        if (CENTRE) {
+            inv.x = rcp_approx(fmaxf(d2.x, 1e-10f));           // rasterization_utils.cuh:37-43 (d2 >= 0)
+            inv.y = rcp_approx(fmaxf(d2.y, 1e-10f));
+            // positive gradients only inside the splat's bounding box: rasterize_points_backward.cu:161-168
+            const float2 gp = *reinterpret_cast<const float2 *>(s_gp + off);
+            const bool rowin = !(fabsf(dy2.x) > ry);
+            g.x += (rowin && colin0) ? gp.x : 0.0f;            // g- and g+ are never both non-zero: exact
+            g.y += (rowin && colin1) ? gp.y : 0.0f;
+        } else {
+            inv.x = rcp_approx(d2.x);                          // >= one pixel away from the point: d2 >> 1e-10
+            inv.y = rcp_approx(d2.y);
+        }
+        float2 w = __fmul2_rn(g, inv);                         // g / max(d2, 1e-10)   (:170-172)
+        w.x = out0 ? 0.0f : w.x;
+        w.y = out1 ? 0.0f : w.y;
+        sw = __fadd2_rn(sw, w);
+        swy = __ffma2_rn(w, dy2, swy);
+        off += side;
+    }
+}
+
+template <bool POW2>
+__global__ void __launch_bounds__(OCC_THREADS)
+occ_tile_kernel(const __grid_constant__ OccTileArgs a) {
+    extern __shared__ __align__(128) unsigned char occ_smem[];
+    const int n = blockIdx.y, tile = blockIdx.x;
+    const int S = a.S, OB = a.OB, side = a.side, R_box = a.R_box;
+    const float r = a.rs[n];
+    if (!occ_fits(r, S, R_box)) return;          // this view is handled by occ_generic_kernel
+    const int64_t tb = (int64_t)n * OB * OB + tile;
+    int beg = a.tile_offsets[tb], end = a.tile_offsets[tb + 1];
+    if (beg == end) return;
+    {
+        // a tile's list is split over up to gridDim.z CTAs so that dense tiles do not serialise on one CTA;
+        // every CTA stages the (small, L2-resident) window itself
+        const int count = end - beg;
+        const int parts = min((int)gridDim.z, (count + OCC_MIN_PART - 1) / OCC_MIN_PART);
+        if ((int)blockIdx.z >= parts) return;
+        const int per = (count + parts - 1) / parts;
+        beg += (int)blockIdx.z * per;
+        end = min(end, beg + per);
+        if (beg >= end) return;
+    }
+    const int plane_elems = side * side + OCC_SLACK;
+    float *s_gm = reinterpret_cast<float *>(occ_smem);
+    float *s_gp = s_gm + plane_elems;
+    float *s_xf = s_gp + plane_elems;                     // side + OCC_SLACK column centres (NDC)
+    float *s_yf = s_xf + side + OCC_SLACK;                // side row centres
+    float4 *s_rec = reinterpret_cast<float4 *>(s_yf + side);
+    unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(s_rec + OCC_RCAP);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ty = tile / OB, tx = tile - ty * OB;
+    const int wx0 = tx * OCC_TILE - R_box, wy0 = ty * OCC_TILE - R_box;   // window origin (NDC-index pixels)
+    const uint32_t bar = smem_u32(s_bar);
+
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    int cnt = min(OCC_RCAP, end - beg);
+    if (warp == 0) {
+        // TMA stage: 2*side row copies (window of both planes; plane padding == R_box so the window origin is
+        // (ty*32, tx*32) in plane coordinates and every row is 16-byte aligned) + this CTA's first record chunk
+        if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)(2 * side * side * 4 + cnt * 16));
+        __syncwarp();
+        const float *src0 = a.planes + (((int64_t)n * 2) * a.Hp + (int64_t)ty * OCC_TILE) * a.W + tx * OCC_TILE;
+        for (int row = lane; row < 2 * side; row += 32) {
+            const int pl = row >= side ? 1 : 0, rr = row - pl * side;
+            const float *src = src0 + ((int64_t)pl * a.Hp + rr) * a.W;
+            bulk_copy_g2s(smem_u32((pl ? s_gp : s_gm) + rr * side), src, (uint32_t)(side * 4), bar);
+        }
+        if (lane == 0) bulk_copy_g2s(smem_u32(s_rec), a.crec + beg, (uint32_t)(cnt * 16), bar);
+    }
+    // exact pixel-centre NDC coordinates of the window's columns / rows (the reference's PixToNdc, division
+    // included, evaluated once per CTA instead of once per pair)
+    for (int i = tid; i < side + OCC_SLACK; i += OCC_THREADS) {
+        s_xf[i] = pix_to_ndc(wx0 + i, S);
+        if (i < side) s_yf[i] = pix_to_ndc(wy0 + i, S);
+    }
+    __syncthreads();
+
+    const int R = occ_halo(r, S);
+    const int Rw = R - 1;                        // per-splat window half-width in pixels (covers the disc)
+    const int Wwin = 2 * Rw + 1;
+    const int need = Wwin + 1;                   // + 1: the window is shifted left to an even column
+    int lps = 4;                                 // lanes per splat; each lane owns two adjacent columns
+    while (2 * lps < need && lps < 32) lps <<= 1;
+    const int ncb = (need + 2 * lps - 1) / (2 * lps);    // column blocks (1 unless the window is > 64 wide)
+    const int groups = 32 / lps;
+    const int grp = lane / lps, gl = lane - grp * lps;
+    const float r2 = r * r;
+    const float half_S = 0.5f * (float)S;
+    const float pixf = 2.0f / (float)S;
+    const float2 pix2 = make_float2(pixf, pixf);
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int NW = OCC_THREADS / 32;
+
+    uint32_t phase = 0;
+    for (int cbase = beg; cbase < end; cbase += OCC_RCAP) {
+        if (cbase > beg) {
+            // next record chunk: everyone is done with the previous one, re-arm the barrier and let the TMA refill
+            __syncthreads();
+            cnt = min(OCC_RCAP, end - cbase);
+            if (tid == 0) {
+                mbar_arrive_expect_tx(bar, (uint32_t)(cnt * 16));
+                bulk_copy_g2s(smem_u32(s_rec), a.crec + cbase, (uint32_t)(cnt * 16), bar);
+            }
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+
+        for (int k0 = warp * groups; k0 < cnt; k0 += NW * groups) {
+            const int k = k0 + grp;
+            const bool have = k < cnt;
+            const float4 rc = s_rec[have ? k : 0];
+            const float px = rc.x, py = rc.y, rx = rc.z, ry = rc.w;
+            // centre pixel, clamped into this tile (it is this tile's by construction; the clamp only absorbs
+            // rounding), and the window origin in staged coordinates (always inside: R_box >= R = Rw + 1)
+            const int cx = min(max(centre_pixel(px, S), tx * OCC_TILE), tx * OCC_TILE + OCC_TILE - 1);
+            const int cy = min(max(centre_pixel(py, S), ty * OCC_TILE), ty * OCC_TILE + OCC_TILE - 1);
+            const int ox = (cx - Rw - wx0) & ~1, oy = cy - Rw - wy0;
+            // rows the splat's own bbox can reach (+1 for rounding) -- at least the 3 rows around the point
+            int bh = have ? min(Rw, (int)fminf(ceilf(ry * half_S) + 1.0f, 4096.0f)) : 0;
+            bh = max(__reduce_max_sync(FULL, bh), min(Rw, 1));
+            const int jc0 = Rw - bh, jc1 = Rw + bh + 1;
+            const float2 npy2 = make_float2(-py, -py);
+            float gx = 0.f, gy = 0.f;
+            for (int cb = 0; cb < ncb; ++cb) {
+                const int sx = ox + cb * 2 * lps + 2 * gl;                  // even
+                const float2 xf = *reinterpret_cast<const float2 *>(s_xf + sx);
+                const float dx0 = xf.x - px, dx1 = xf.y - px;
+                const float2 dxsq = make_float2(dx0 * dx0, dx1 * dx1);
+                const bool colin0 = !(fabsf(dx0) > rx), colin1 = !(fabsf(dx1) > rx);
+                float2 sw = make_float2(0.f, 0.f), swy = make_float2(0.f, 0.f);
+                const float yfm1 = s_yf[oy] - pixf;                        // row -1 (POW2: exact)
+                float2 yf2 = make_float2(yfm1, yfm1);
+                const int off = oy * side + sx;
+                occ_rows<false, POW2>(0, jc0, s_gm, s_gp, s_yf + oy, side, off, yf2, pix2, npy2, dxsq, ry, colin0, colin1,
+                                      r2, sw, swy);
+                occ_rows<true, POW2>(jc0, jc1, s_gm, s_gp, s_yf + oy, side, off + jc0 * side, yf2, pix2, npy2, dxsq, ry,
+                                     colin0, colin1, r2, sw, swy);
+                occ_rows<false, POW2>(jc1, Wwin, s_gm, s_gp, s_yf + oy, side, off + jc1 * side, yf2, pix2, npy2, dxsq, ry,
+                                      colin0, colin1, r2, sw, swy);
+                gx = fmaf(dx0, sw.x, fmaf(dx1, sw.y, gx));                 // sum_rows dx*w = dx * sum_rows w
+                gy += swy.x + swy.y;
+            }
+            for (int d = lps >> 1; d > 0; d >>= 1) {
+                gx += __shfl_xor_sync(FULL, gx, d);
+                gy += __shfl_xor_sync(FULL, gy, d);
+            }
+            // rasterize_points_backward.cu:145 -- points outside the renderable area get no gradient
+            if (have && gl == 0 && !(fabsf(py) > 1.0f || fabsf(px) > 1.0f))
+                a.grad_xy[a.cids[cbase + k]] = make_float2(gx, gy);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Generic gather for views whose window does not fit the staged box (very large search radius): one warp per
+// visible splat, lanes stride over the (2R+1)^2 pixel window in global memory, the reference's per-pair rule
+// (rasterize_points_backward.cu:141-178), warp reduction.
+// ---------------------------------------------------------------------------------------------
+constexpr int OCC_WARPS = 8;
+
+__global__ void __launch_bounds__(OCC_WARPS * 32)
+occ_generic_kernel(const float4 *__restrict__ rec, const uint8_t *__restrict__ visible,
+                   const float *__restrict__ rs, const float *__restrict__ grad, int pix_stride,
+                   int pix_offset, const int64_t *__restrict__ first_idx,
+                   const int64_t *__restrict__ num_points, int64_t P0_shared, int S, int R_box,
+                   float2 *__restrict__ grad_xy) {
+    const int n = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const ViewRange vr = view_range(first_idx, num_points, n, P0_shared);
+    const float r = rs[n];
+    if (occ_fits(r, S, R_box)) return;   // this view is handled by occ_tile_kernel
+    const float r2 = r * r;
+    const bool pow2 = (S & (S - 1)) == 0;
+    const float inv_S = 1.0f / (float)S;
+    const float half_S = 0.5f * (float)S;
+    const float *gview = grad + ((int64_t)n * S * S) * pix_stride + pix_offset;
+    constexpr unsigned FULL = 0xffffffffu;
+
+    for (int64_t g0 = ((int64_t)blockIdx.x * OCC_WARPS + warp) * 32; g0 < vr.count;
+         g0 += (int64_t)gridDim.x * OCC_WARPS * 32) {
+        const int64_t i = g0 + lane;
+        const bool in_range = i < vr.count;
+        const int64_t p = vr.first + i;
+        float4 A = make_float4(0.f, 0.f, -1.f, 0.f);
+        float ry = 0.f;
+        bool vis = false;
+        if (in_range) {
+            vis = visible[p] != 0;
+            if (vis) {
+                A = __ldg(&rec[2 * p]);
+                ry = __ldg(&rec[2 * p + 1]).x;
+                // rasterize_points_backward.cu:145 -- outside the renderable area
+                if (A.z < 0.0f || fabsf(A.y) > 1.0f || fabsf(A.x) > 1.0f) vis = false;
+            }
+        }
+        float out_x = 0.f, out_y = 0.f;
+        unsigned todo = __ballot_sync(FULL, vis);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const float px = __shfl_sync(FULL, A.x, src);
+            const float py = __shfl_sync(FULL, A.y, src);
+            const float rx = __shfl_sync(FULL, A.w, src);
+            const float ryb = __shfl_sync(FULL, ry, src);
+            // conservative window in NDC-index space: pixel i has centre -1 + (2i+1)/S
+            // (clamped in float first: saturating conversions of huge radii must not wrap)
+            const float top = (float)(S - 1);
+            const int xi_lo = (int)fminf(fmaxf(floorf((px - r + 1.0f) * half_S - 0.5f) - 1.0f, 0.0f), top + 1.0f);
+            const int xi_hi = (int)fmaxf(fminf(ceilf((px + r + 1.0f) * half_S - 0.5f) + 1.0f, top), -1.0f);
+            const int yi_lo = (int)fminf(fmaxf(floorf((py - r + 1.0f) * half_S - 0.5f) - 1.0f, 0.0f), top + 1.0f);
+            const int yi_hi = (int)fmaxf(fminf(ceilf((py + r + 1.0f) * half_S - 0.5f) + 1.0f, top), -1.0f);
+            const int W = xi_hi - xi_lo + 1, H = yi_hi - yi_lo + 1;
+            float gx = 0.f, gy = 0.f;
+            if (W > 0 && H > 0) {
+                const int total = W * H;
+                int wy = lane / W, wx = lane - wy * W;
+                const int step_y = 32 / W, step_x = 32 - step_y * W;
+                for (int w = lane; w < total; w += 32) {
+                    const int xi = xi_lo + wx, yi = yi_lo + wy;
+                    const float g = __ldg(gview + ((int64_t)(S - 1 - yi) * S + (S - 1 - xi)) * pix_stride);
+                    if (g != 0.0f) {
+                        const float xf = pix_to_ndc_fast(xi, S, inv_S, pow2);
+                        const float yf = pix_to_ndc_fast(yi, S, inv_S, pow2);
+                        const float dx = xf - px, dy = yf - py;
+                        const float d2 = dx * dx + dy * dy;
+                        const bool outside = (fabsf(dx) > rx) || (fabsf(dy) > ryb);
+                        if (!(d2 > r2) && !(g > 0.0f && outside)) {
+                            const float den = eps_denom(d2, 1e-10f);
+                            gx += dx / den * g;
+                            gy += dy / den * g;
+                        }
+                    }
+                    wx += step_x;
+                    wy += step_y;
+                    if (wx >= W) {
+                        wx -= W;
+                        wy += 1;
+                    }
+                }
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                gx += __shfl_xor_sync(FULL, gx, d);
+                gy += __shfl_xor_sync(FULL, gy, d);
+            }
+            if (lane == src) {
+                out_x = gx;
+                out_y = gy;
+            }
+        }
+        if (in_range) grad_xy[p] = make_float2(out_x, out_y);
+    }
+}
+
+// rs: (N,) search radii -- an INPUT when radii_s < 0 (the _C-level op passes them in), otherwise computed here as
+// radii_s * lower median of the visible radii and written to rs.  grad_xy (P,2) is fully written.
+int occ_backward(dss_ctx *ctx, const float4 *rec, const uint8_t *visible, float *rs, float radii_s,
+                 const float *grad_occ, int pix_stride, int pix_offset, const int64_t *first_idx,
+                 const int64_t *num_points, int N, int64_t P0, int S, float *grad_xy, cudaStream_t st) {
+    if (N <= 0 || P0 <= 0) return DSS_OK;
+    const int OB = (S + OCC_TILE - 1) / OCC_TILE;
+    const int64_t nt = (int64_t)N * OB * OB;
+    const int64_t Ptot = (first_idx == nullptr) ? (int64_t)N * P0 : P0;   // packed mode passes P0 = P
+    const bool compute_rs = radii_s >= 0.0f;
+    // Size of the staged window from the radii seen by the previous call (a hint only: both kernels re-derive
+    // "fits" from the current radius on the device, views that do not fit take the generic kernel)
+    float *h_rs = reinterpret_cast<float *>(ctx->h_pinned + 8);
+    float hint = 0.0f;
+    for (int i = 0; i < (N < 96 ? N : 96); ++i) hint = fmaxf(hint, h_rs[i]);
+    int R_box = 20;
+    if (hint > 0.0f && hint < 4.0f) R_box = (occ_halo(hint * 1.15f, S) + 1 + 3) & ~3;
+    if (R_box < 8) R_box = 8;
+    if (R_box > OCC_RBOX_MAX) R_box = OCC_RBOX_MAX;
+    const int side = OCC_TILE + 2 * R_box;
+    const size_t smem = (size_t)(2 * (side * side + OCC_SLACK) + 2 * side + OCC_SLACK) * sizeof(float) +
+                        (size_t)OCC_RCAP * sizeof(float4) + 16;
+    const bool tiles_ok = (size_t)OB * OB * sizeof(int32_t) <= 200 * 1024 && nt + 1 < (int64_t)INT32_MAX &&
+                          Ptot < (int64_t)INT32_MAX;
+    if (!tiles_ok) R_box = 0;
+    int rc;
+    DSS_CUDA_TRY(cudaMemsetAsync(grad_xy, 0, (size_t)Ptot * 2 * sizeof(float), st));
+    if (R_box > 0) {
+        int32_t *counts = nullptr, *offsets = nullptr, *cids = nullptr;
+        float4 *crec = nullptr;
+        float *planes = nullptr;
+        const int PAD = R_box, W = OB * OCC_TILE + 2 * PAD, Hp = W;
+        if ((rc = ctx_get(ctx, BUF_TILE_COUNTS, (size_t)(nt + 1), &counts))) return rc;
+        if ((rc = ctx_get(ctx, BUF_TILE_OFFSETS, (size_t)(nt + 1), &offsets))) return rc;
+        if ((rc = ctx_get(ctx, BUF_TILE_IDS, (size_t)(Ptot > 0 ? Ptot : 1), &cids))) return rc;
+        if ((rc = ctx_get(ctx, BUF_OCC_REC, (size_t)(Ptot > 0 ? Ptot : 1), &crec))) return rc;
+        if ((rc = ctx_get(ctx, BUF_OCC_PLANES, (size_t)N * 2 * Hp * W, &planes))) return rc;
+        {
+            StageScope prof(ctx, ST_OCC_BIN, st);
+            DSS_CUDA_TRY(cudaMemsetAsync(counts, 0, (size_t)(nt + 1) * sizeof(int32_t), st));
+            dim3 bgrid((unsigned)((P0 + 2047) / 2048), N);
+            const size_t hist = (size_t)OB * OB * sizeof(int32_t);
+            if (hist > 48 * 1024) {
+                DSS_CUDA_TRY(cudaFuncSetAttribute(occ_bin_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist));
+                DSS_CUDA_TRY(cudaFuncSetAttribute(occ_bin_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist));
+            }
+            occ_bin_kernel<0><<<bgrid, 256, hist, st>>>(rec, visible, first_idx, num_points, P0, S, OB, counts, nullptr, nullptr);
+            DSS_LAUNCH_CHECK(ctx);
+            if ((rc = exclusive_scan_i32(ctx, counts, offsets, nt + 1, st))) return rc;
+            DSS_CUDA_TRY(cudaMemcpyAsync(counts, offsets, (size_t)nt * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+            occ_bin_kernel<1><<<bgrid, 256, hist, st>>>(rec, visible, first_idx, num_points, P0, S, OB, counts, crec, cids);
+            DSS_LAUNCH_CHECK(ctx);
+        }
+        if (compute_rs) {
+            unsigned int *hist = nullptr;
+            if ((rc = ctx_get(ctx, BUF_SELECT, (size_t)N * 4 * 256, &hist))) return rc;
+            StageScope prof(ctx, ST_SEARCH_RADIUS, st);
+            DSS_CUDA_TRY(cudaMemsetAsync(hist, 0, (size_t)N * 4 * 256 * sizeof(unsigned int), st));
+            dim3 grid(occ_nblocks(P0 / 4 + 1, 256, ctx->sm_count, 1), N);
+            for (int pass = 0; pass < 4; ++pass) {
+                select_hist_compact_kernel<<<grid, 256, 0, st>>>(crec, offsets, OB * OB, pass, hist);
+                DSS_LAUNCH_CHECK(ctx);
+            }
+            select_final_kernel<<<N, 32, 0, st>>>(hist, radii_s, rs);
+            DSS_LAUNCH_CHECK(ctx);
+        }
+        StageScope prof(ctx, ST_OCC_BWD, st);
+        {
+            dim3 pgrid((unsigned)((W + 255) / 256), (unsigned)Hp, (unsigned)N);
+            occ_planes_kernel<<<pgrid, 256, 0, st>>>(grad_occ, pix_stride, pix_offset, S, PAD, W, Hp, planes);
+            DSS_LAUNCH_CHECK(ctx);
+        }
+        OccTileArgs a;
+        a.crec = crec;
+        a.cids = cids;
+        a.tile_offsets = offsets;
+        a.rs = rs;
+        a.planes = planes;
+        a.grad_xy = reinterpret_cast<float2 *>(grad_xy);
+        a.S = S;
+        a.OB = OB;
+        a.R_box = R_box;
+        a.side = side;
+        a.W = W;
+        a.Hp = Hp;
+        const bool pow2 = (S & (S - 1)) == 0;
+        dim3 tgrid((unsigned)(OB * OB), N, OCC_MAX_PARTS);
+        if (pow2) {
+            DSS_CUDA_TRY(cudaFuncSetAttribute(occ_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            occ_tile_kernel<true><<<tgrid, OCC_THREADS, smem, st>>>(a);
+        } else {
+            DSS_CUDA_TRY(cudaFuncSetAttribute(occ_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            occ_tile_kernel<false><<<tgrid, OCC_THREADS, smem, st>>>(a);
+        }
+        DSS_LAUNCH_CHECK(ctx);
+    } else if (compute_rs) {
+        if ((rc = search_radius(ctx, rec, nullptr, visible, first_idx, num_points, N, P0, radii_s, rs, st))) return rc;
+    }
+    {
+        // views whose window does not fit (very large search radius) take the direct global-memory gather
+        StageScope prof(ctx, ST_OCC_BWD, st);
+        dim3 grid(occ_nblocks(P0, OCC_WARPS * 32, ctx->sm_count, 64), N);
+        occ_generic_kernel<<<grid, OCC_WARPS * 32, 0, st>>>(rec, visible, rs, grad_occ, pix_stride, pix_offset, first_idx,
+                                                            num_points, P0, S, R_box,
+                                                            reinterpret_cast<float2 *>(grad_xy));
+        DSS_LAUNCH_CHECK(ctx);
+    }
+    // refresh the hint for the next call (asynchronous; may be read stale, it is only a hint)
+    DSS_CUDA_TRY(cudaMemcpyAsync(h_rs, rs, (size_t)(N < 96 ? N : 96) * sizeof(float), cudaMemcpyDeviceToHost, st));
+    return DSS_OK;
+}
+
+}  // namespace dss
+
+extern "C" {
+
+int dss_search_radius(dss_ctx *ctx, const float *radii, const uint8_t *visible, const int64_t *first_idx,
+                      const int64_t *num_points, int N, int64_t P, float radii_s, float *rs, void *stream) {
+    DSS_REQUIRE(ctx != nullptr, "ctx is null");
+    DSS_REQUIRE(N >= 0 && P >= 0, "negative size");
+    if (N == 0) return DSS_OK;
+    DSS_REQUIRE(rs && first_idx && num_points && (P == 0 || (radii && visible)), "null pointer");
+    return dss::search_radius(ctx, nullptr, radii, visible, first_idx, num_points, N, P, radii_s, rs,
+                              (cudaStream_t)stream);
+}
+
+int dss_occ_backward(dss_ctx *ctx, const float *points, const float *radii, const uint8_t *visible,
+                     const float *rs, const float *grad_occ, int pix_stride, int pix_offset,
+                     const int64_t *first_idx, const int64_t *num_points, int N, int64_t P, int image_size,
+                     float *grad_xy, void *stream) {
+    using namespace dss;
+    cudaStream_t st = (cudaStream_t)stream;
+    DSS_REQUIRE(ctx != nullptr, "ctx is null");
+    DSS_REQUIRE(N >= 0 && P >= 0 && image_size > 0, "bad size");
+    DSS_REQUIRE(pix_stride >= 1 && pix_offset >= 0 && pix_offset < pix_stride, "bad pixel stride/offset");
+    if (N == 0 || P == 0) return DSS_OK;
+    DSS_REQUIRE(points && radii && visible && rs && grad_occ && first_idx && num_points && grad_xy, "null pointer");
+    float4 *rec = nullptr;
+    int rc;
+    if ((rc = ctx_get(ctx, BUF_RECORDS, (size_t)(2 * P), &rec))) return rc;
+    if ((rc = pack_records(ctx, points, radii, nullptr, P, rec, st))) return rc;
+    return occ_backward(ctx, rec, visible, const_cast<float *>(rs), -1.0f, grad_occ, pix_stride, pix_offset, first_idx,
+                        num_points, N, P, image_size, grad_xy, st);
+}
+
+}  // extern "C"

@@ -371,13 +371,11 @@ int dss_render_backward(dss_ctx *ctx, const dss_render_args *g, void *stream) {
     }
     if ((rc = ctx_get(ctx, BUF_RS, (size_t)N, &rs))) return rc;
     if ((rc = ctx_get(ctx, BUF_GRADXY, (size_t)(2 * P), &gxy))) return rc;
-    if ((rc = search_radius(ctx, rec, nullptr, g->visible, fi, g->num_points, N, g->P0, g->radii_backward_scaler,
-                            rs, st)))
+    if ((rc = occ_backward(ctx, rec, g->visible, rs, g->radii_backward_scaler, g->grad_image, 4, 3, fi, g->num_points, N,
+                           g->P0, S, gxy, st)))
         return rc;
     if (g->search_radius)
         DSS_CUDA_TRY(cudaMemcpyAsync(g->search_radius, rs, (size_t)N * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    if ((rc = occ_backward(ctx, rec, g->visible, rs, g->grad_image, 4, 3, fi, g->num_points, N, g->P0, S, gxy, st)))
-        return rc;
     if (g->grad_colours) {
         DSS_CUDA_TRY(cudaMemsetAsync(g->grad_colours, 0, (size_t)P * 3 * sizeof(float), st));
         if ((rc = colour_backward(ctx, g->idx, g->weights, g->grad_image, npix, K, g->grad_colours, st))) return rc;
