@@ -38,6 +38,7 @@ class RenderArgs(C.Structure):
         ("idx", vp), ("weights", vp), ("zbuf", vp), ("qvalue", vp), ("visible", vp),
         ("grad_image", vp), ("grad_zbuf", vp), ("grad_colours", vp), ("grad_ndc", vp),
         ("grad_points_world", vp), ("search_radius", vp),
+        ("shared_colours", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 

@@ -77,7 +77,7 @@ int zbuf_backward(dss_ctx *ctx, const int32_t *idx, const float *grad_zbuf, int6
 __global__ void __launch_bounds__(256)
 colour_backward_kernel(const int32_t *__restrict__ idx, const float *__restrict__ weights,
                        const float4 *__restrict__ grad_image, int64_t num_pixels, int K,
-                       float *grad_colours) {
+                       float *grad_colours, int64_t colour_P0, int64_t pixels_per_view) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < num_pixels;
          i += (int64_t)gridDim.x * blockDim.x) {
         if (idx[i * K] < 0) continue;
@@ -87,7 +87,7 @@ colour_backward_kernel(const int32_t *__restrict__ idx, const float *__restrict_
             const int p = idx[i * K + k];
             if (p < 0) break;
             const float w = weights[i * K + k];
-            float *dst = grad_colours + (int64_t)p * 3;
+            float *dst = grad_colours + ((int64_t)p - (colour_P0 > 0 ? (i / pixels_per_view) * colour_P0 : 0)) * 3;
             atomicAdd(dst + 0, g.x * w);
             atomicAdd(dst + 1, g.y * w);
             atomicAdd(dst + 2, g.z * w);
@@ -96,11 +96,12 @@ colour_backward_kernel(const int32_t *__restrict__ idx, const float *__restrict_
 }
 
 int colour_backward(dss_ctx *ctx, const int32_t *idx, const float *weights, const float *grad_image,
-                    int64_t num_pixels, int K, float *grad_colours, cudaStream_t st) {
+                    int64_t num_pixels, int K, float *grad_colours, int64_t colour_P0, int64_t pixels_per_view,
+                    cudaStream_t st) {
     if (num_pixels == 0) return DSS_OK;
     StageScope prof(ctx, ST_COLOUR_BWD, st);
     colour_backward_kernel<<<nblocks(num_pixels, 256, ctx->sm_count, 16), 256, 0, st>>>(
-        idx, weights, reinterpret_cast<const float4 *>(grad_image), num_pixels, K, grad_colours);
+        idx, weights, reinterpret_cast<const float4 *>(grad_image), num_pixels, K, grad_colours, colour_P0, pixels_per_view);
     DSS_LAUNCH_CHECK(ctx);
     return DSS_OK;
 }

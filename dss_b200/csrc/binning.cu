@@ -156,12 +156,17 @@ int compute_zrange(dss_ctx *ctx, const float4 *rec, const int64_t *first_idx, co
 // Fallback (plain global atomics) when the histogram of B*B tiles does not fit in shared memory.
 // ---------------------------------------------------------------------------------------------
 constexpr int BIN_THREADS = 256;
-constexpr int BIN_ITEMS = 16;
+constexpr int BIN_ITEMS = 16;   // splats per thread (32 measured slower: fewer, longer blocks)
 constexpr int BIN_CHUNK = BIN_THREADS * BIN_ITEMS;
 constexpr int BIN_MAX_SMEM_TILES = 48 * 1024;   // 192 KB of histogram at most
 
-__device__ __forceinline__ int2 pack_rect(const BinRect &r) {
-    return r.empty ? make_int2(-1, -1) : make_int2(r.x0 | (r.x1 << 16), r.y0 | (r.y1 << 16));
+// tile rectangle + depth slice of a splat in one register: 7 bits per coordinate (B <= 128), 4 bits of slice
+constexpr int BIN_PACK_MAX_B = 128;
+constexpr unsigned int BIN_PACK_EMPTY = 0xffffffffu;
+__device__ __forceinline__ unsigned int pack_rect(const BinRect &r, int slice) {
+    return r.empty ? BIN_PACK_EMPTY
+                   : (unsigned int)r.x0 | ((unsigned int)r.x1 << 7) | ((unsigned int)r.y0 << 14) | ((unsigned int)r.y1 << 21) |
+                         ((unsigned int)slice << 28);
 }
 
 template <bool SMEM>
@@ -211,7 +216,8 @@ template <bool SMEM>
 __global__ void __launch_bounds__(BIN_THREADS)
 bin_scatter_kernel(const float4 *__restrict__ rec, const int64_t *__restrict__ first_idx,
                    const int64_t *__restrict__ num_points, int64_t P0_shared, int S, int bin, int B, int NS,
-                   const float *__restrict__ zrange, int32_t *__restrict__ cursors, int32_t *__restrict__ ids) {
+                   const float *__restrict__ zrange, int32_t *__restrict__ cursors, int32_t *__restrict__ ids,
+                   int ids_capacity) {
     extern __shared__ int32_t s_hist[];
     const int n = blockIdx.y;
     const int nt = B * B * NS;
@@ -224,29 +230,27 @@ bin_scatter_kernel(const float4 *__restrict__ rec, const int64_t *__restrict__ f
         for (int t = threadIdx.x; t < nt; t += BIN_THREADS) s_hist[t] = 0;
         __syncthreads();
     }
-    int2 rect[BIN_ITEMS];
-    int slice[BIN_ITEMS];
+    unsigned int rect[SMEM ? BIN_ITEMS : 1];
 #pragma unroll
     for (int j = 0; j < BIN_ITEMS; ++j) {
-        rect[j] = make_int2(-1, -1);
-        slice[j] = 0;
+        if (SMEM) rect[j] = BIN_PACK_EMPTY;
         const int64_t i = chunk0 + j * BIN_THREADS + threadIdx.x;
         if (i < vr.count) {
             const int64_t p = vr.first + i;
             const float4 A = __ldg(&rec[2 * p]);
             const float ry = __ldg(&rec[2 * p + 1]).x;
             const BinRect r = splat_bin_rect(A, ry, bin, S, B);
-            rect[j] = pack_rect(r);
             if (!r.empty) {
-                slice[j] = depth_slice(sm, A.z);
+                const int sl = depth_slice(sm, A.z);
+                if (SMEM) rect[j] = pack_rect(r, sl);
                 for (int by = r.y0; by <= r.y1; ++by)
                     for (int bx = r.x0; bx <= r.x1; ++bx) {
-                        const int key = (by * B + bx) * NS + slice[j];
+                        const int key = (by * B + bx) * NS + sl;
                         if (SMEM) {
                             atomicAdd(&s_hist[key], 1);
                         } else {
                             const int slot = atomicAdd(&cur[key], 1);
-                            ids[slot] = (int32_t)p;
+                            if (slot < ids_capacity) ids[slot] = (int32_t)p;
                         }
                     }
             }
@@ -262,13 +266,14 @@ bin_scatter_kernel(const float4 *__restrict__ rec, const int64_t *__restrict__ f
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < BIN_ITEMS; ++j) {
-        if (rect[j].x < 0) continue;
-        const int x0 = rect[j].x & 0xffff, x1 = rect[j].x >> 16, y0 = rect[j].y & 0xffff, y1 = rect[j].y >> 16;
+        const unsigned int pr = rect[j];
+        if (pr == BIN_PACK_EMPTY) continue;
+        const int x0 = pr & 127, x1 = (pr >> 7) & 127, y0 = (pr >> 14) & 127, y1 = (pr >> 21) & 127, sl = pr >> 28;
         const int32_t p = (int32_t)(vr.first + chunk0 + j * BIN_THREADS + threadIdx.x);
         for (int by = y0; by <= y1; ++by)
             for (int bx = x0; bx <= x1; ++bx) {
-                const int slot = atomicAdd(&s_hist[(by * B + bx) * NS + slice[j]], 1);
-                ids[slot] = p;
+                const int slot = atomicAdd(&s_hist[(by * B + bx) * NS + sl], 1);
+                if (slot < ids_capacity) ids[slot] = p;
             }
     }
 }
@@ -288,10 +293,13 @@ static int prepare_smem(Kern kern, size_t bytes) {
     return DSS_OK;
 }
 
-// Number of depth slices such that the per-block histogram (B*B*NS ints) fits in shared memory.
+// Number of depth slices of the forward tile lists.  Measured on the 1M-point / 512^2 workload (bench.py): the
+// rasterizer is as fast with 8 slices as with 16 (early termination is decided per chunk of the list anyway) and the
+// binning histograms are half as large; more tiles -> fewer slices so that the per-block histogram (B*B*NS ints)
+// stays within 32 KB of shared memory.
 int choose_depth_slices(int B) {
-    int ns = 16;
-    while (ns > 1 && (int64_t)B * B * ns > 32 * 1024) ns >>= 1;   // <= 128 KB of histogram
+    int ns = 8;
+    while (ns > 1 && (int64_t)B * B * ns > 8 * 1024) ns >>= 1;
     return ns;
 }
 
@@ -305,7 +313,7 @@ int bin_count_and_scan(dss_ctx *ctx, const float4 *rec, const int64_t *first_idx
     if (P0 > 0) {
         dim3 grid((unsigned)((P0 + BIN_CHUNK - 1) / BIN_CHUNK), N);
         StageScope prof(ctx, ST_BIN_COUNT, st);
-        if ((int64_t)B * B * NS <= BIN_MAX_SMEM_TILES && B < 32768 && !ctx->bin_direct) {
+        if ((int64_t)B * B * NS <= BIN_MAX_SMEM_TILES && B <= BIN_PACK_MAX_B && NS <= 16 && !ctx->bin_direct) {
             const size_t smem = (size_t)B * B * NS * sizeof(int32_t);
             int rc = prepare_smem(bin_count_kernel<true>, smem);
             if (rc) return rc;
@@ -320,20 +328,21 @@ int bin_count_and_scan(dss_ctx *ctx, const float4 *rec, const int64_t *first_idx
 
 int bin_scatter(dss_ctx *ctx, const float4 *rec, const int64_t *first_idx, const int64_t *num_points, int N,
                 int64_t P0, int S, int bin, int NS, const float *zrange, const int32_t *offsets, int32_t *cursors,
-                int32_t *ids, cudaStream_t st) {
+                int32_t *ids, int64_t ids_capacity, cudaStream_t st) {
     const int B = 1 + (S - 1) / bin;
     const int64_t nb = (int64_t)N * B * B * NS;
+    const int cap = (int)(ids_capacity > (int64_t)INT32_MAX ? (int64_t)INT32_MAX : ids_capacity);
     DSS_CUDA_TRY(cudaMemcpyAsync(cursors, offsets, (size_t)nb * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
     if (P0 > 0) {
         dim3 grid((unsigned)((P0 + BIN_CHUNK - 1) / BIN_CHUNK), N);
         StageScope prof(ctx, ST_BIN_SCATTER, st);
-        if ((int64_t)B * B * NS <= BIN_MAX_SMEM_TILES && B < 32768 && !ctx->bin_direct) {
+        if ((int64_t)B * B * NS <= BIN_MAX_SMEM_TILES && B <= BIN_PACK_MAX_B && NS <= 16 && !ctx->bin_direct) {
             const size_t smem = (size_t)B * B * NS * sizeof(int32_t);
             int rc = prepare_smem(bin_scatter_kernel<true>, smem);
             if (rc) return rc;
-            bin_scatter_kernel<true><<<grid, BIN_THREADS, smem, st>>>(rec, first_idx, num_points, P0, S, bin, B, NS, zrange, cursors, ids);
+            bin_scatter_kernel<true><<<grid, BIN_THREADS, smem, st>>>(rec, first_idx, num_points, P0, S, bin, B, NS, zrange, cursors, ids, cap);
         } else {
-            bin_scatter_kernel<false><<<grid, BIN_THREADS, 0, st>>>(rec, first_idx, num_points, P0, S, bin, B, NS, zrange, cursors, ids);
+            bin_scatter_kernel<false><<<grid, BIN_THREADS, 0, st>>>(rec, first_idx, num_points, P0, S, bin, B, NS, zrange, cursors, ids, cap);
         }
         DSS_LAUNCH_CHECK(ctx);
     }
@@ -441,7 +450,8 @@ int dss_rasterize_coarse(dss_ctx *ctx, const float *points, const float *radii, 
         return DSS_E_CAPACITY;
     }
     if (total == 0) return DSS_OK;
-    return bin_scatter(ctx, rec, first_idx, num_points, N, P, S, bin_size, 1, nullptr, bin_offsets, counts, bin_ids, st);
+    return bin_scatter(ctx, rec, first_idx, num_points, N, P, S, bin_size, 1, nullptr, bin_offsets, counts, bin_ids,
+                       bin_ids_capacity, st);
 }
 
 }  // extern "C"

@@ -57,6 +57,10 @@ enum BufId {
     BUF_STATS,
     BUF_OCC_REC,      // compact tile-ordered {px,py,rx,ry} of the visible splats (occupancy backward)
     BUF_OCC_PLANES,   // zero-padded g-/g+ planes of the alpha gradient
+    BUF_OCC_PARTS,    // work items per tile and their exclusive scan
+    BUF_OCC_ITEMS,    // tile of every work item
+    BUF_OCC_COUNTS,   // per-tile counters of the occupancy binning (kept at zero between calls)
+    BUF_OCC_IDS,      // packed splat id of every compact record
     NUM_BUFS
 };
 
@@ -87,6 +91,15 @@ struct dss_ctx {
     int n_pending, cap_pending;
     int open[8], n_open;
     int raster_stats;   // debug: accumulate raster work counters
+    int raster_minb5;   // tuning (env DSS_RASTER_MINB=5): 5 resident CTAs/SM (48 registers) instead of 4 (64)
+    int sync_forward;   // tuning (env DSS_SYNC_FORWARD=1): always wait for the tile-list size before the scatter
+    cudaEvent_t ev_total;   // marks the read-back of the tile-list size
+    cudaStream_t side;      // second stream: independent backward work (colour scatter) overlaps the occupancy path
+    cudaEvent_t ev_fork, ev_join;
+    const void *occ_counts_ptr;   // BUF_OCC_COUNTS block known to be all zero (nullptr: unknown)
+    size_t occ_counts_elems;
+    int occ_lps8;           // tuning (env DSS_OCC_LPS8=1): 8 lanes x 2 column pairs per splat instead of 4 x 4
+    int ns_override;    // tuning (env DSS_NS): number of depth slices of the forward tile lists, 0 = automatic
     int bin_direct;     // tuning (env DSS_BIN_DIRECT): tile binning with plain global atomics instead of per-block histograms
     double stage_ms[dss::NUM_STAGES];
     int64_t stage_calls[dss::NUM_STAGES];

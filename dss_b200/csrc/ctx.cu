@@ -266,6 +266,12 @@ int dss_create(dss_ctx **out) {
     {
         const char *e = getenv("DSS_BIN_DIRECT");
         c->bin_direct = (e && e[0] == '1') ? 1 : 0;
+        const char *mb = getenv("DSS_RASTER_MINB");
+        c->raster_minb5 = (mb && mb[0] == '5') ? 1 : 0;
+        const char *sf = getenv("DSS_SYNC_FORWARD");
+        c->sync_forward = (sf && sf[0] == '1') ? 1 : 0;
+        const char *ns = getenv("DSS_NS");
+        c->ns_override = ns ? atoi(ns) : 0;
     }
     if (cudaMallocHost((void **)&c->h_pinned, 64 * sizeof(int64_t)) != cudaSuccess) {
         cudaGetLastError();
@@ -274,6 +280,20 @@ int dss_create(dss_ctx **out) {
         return DSS_E_NOMEM;
     }
     memset(c->h_pinned, 0, 64 * sizeof(int64_t));
+    {
+        const char *l8 = getenv("DSS_OCC_LPS8");
+        c->occ_lps8 = (l8 && l8[0] == '1') ? 1 : 0;
+    }
+    if (cudaEventCreateWithFlags(&c->ev_total, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFreeHost(c->h_pinned);
+        delete c;
+        dss::set_error("event creation failed");
+        return DSS_E_CUDA;
+    }
     *out = c;
     return DSS_OK;
 }
@@ -288,6 +308,10 @@ void dss_destroy(dss_ctx *ctx) {
     for (int i = 0; i < dss::NUM_BUFS; ++i)
         if (ctx->buf[i]) cudaFree(ctx->buf[i]);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->ev_total) cudaEventDestroy(ctx->ev_total);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->side) cudaStreamDestroy(ctx->side);
     delete ctx;
 }
 

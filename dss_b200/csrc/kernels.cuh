@@ -22,7 +22,7 @@ int bin_count_and_scan(dss_ctx *ctx, const float4 *rec, const int64_t *first_idx
 
 int bin_scatter(dss_ctx *ctx, const float4 *rec, const int64_t *first_idx, const int64_t *num_points, int N,
                 int64_t P0, int S, int bin, int NS, const float *zrange, const int32_t *offsets, int32_t *cursors,
-                int32_t *ids, cudaStream_t st);
+                int32_t *ids, int64_t ids_capacity, cudaStream_t st);
 
 // Depth slicing shared by the binning and raster kernels (identical arithmetic on both sides).
 struct SliceMap {
@@ -62,6 +62,7 @@ struct RasterArgs {
     float cutoff_uniform;
     const int32_t *tile_offsets;  // (N*B*B + 1)
     const int32_t *tile_ids;
+    int ids_capacity;             // entries tile_ids can hold (lists are clamped to it, see bin_and_raster)
     int N, S, K, B;
     int NS;                       // depth slices per tile list
     const float *zrange;          // (N,2) depth range per view (NS > 1)
@@ -73,10 +74,12 @@ struct RasterArgs {
     float *occ;      // may be null (N,S,S)
     // blend (all null when not blending)
     const float *scaler;   // (P,)
-    const float *colours;  // (P,3)
+    const float *colours;  // (P,3), or (P0,3) shared by every view when colour_P0 > 0
+    int64_t colour_P0;     // > 0: colour row of packed splat id in view n is id - n * colour_P0
     float *image;          // (N,S,S,4)
     float *weights;        // (N,S,S,K)
     uint8_t *visible;      // (P,) must be zeroed by the caller
+    int64_t visible_count; // P (to re-zero `visible` when a pass has to be repeated)
     int force_pixel_parallel;  // testing: use the pixel-parallel kernel even for K <= 8
     unsigned long long *stats; // optional debug counters (dss_debug_raster_stats) or nullptr
 };
@@ -98,7 +101,9 @@ int occ_backward(dss_ctx *ctx, const float4 *rec, const uint8_t *visible, float 
                  const int64_t *num_points, int N, int64_t P0, int S, float *grad_xy, cudaStream_t st);
 int zbuf_backward(dss_ctx *ctx, const int32_t *idx, const float *grad_zbuf, int64_t num_pixels, int K,
                   float *z_grad, int z_stride, cudaStream_t st);
+// colour_P0 > 0: grad_colours is (P0,3) shared by the views (pixels_per_view = S*S locates a pixel's view)
 int colour_backward(dss_ctx *ctx, const int32_t *idx, const float *weights, const float *grad_image,
-                    int64_t num_pixels, int K, float *grad_colours, cudaStream_t st);
+                    int64_t num_pixels, int K, float *grad_colours, int64_t colour_P0, int64_t pixels_per_view,
+                    cudaStream_t st);
 
 }  // namespace dss

@@ -26,21 +26,12 @@
 namespace dss {
 
 constexpr int OCC_TILE = 32;            // pixels per side of a backward tile
-constexpr int OCC_THREADS = 256;
-constexpr int OCC_RCAP = 128;           // records staged per TMA chunk
+constexpr int OCC_CONSUMERS = 8;        // consumer warps of the tile kernel (+ 1 producer warp)
+constexpr int OCC_THREADS = (OCC_CONSUMERS + 1) * 32;
+constexpr int OCC_ITEM = 128;           // splats per work item (= records staged per TMA copy)
+constexpr int OCC_GROUP = 4;            // consecutive items handed to one CTA
 constexpr int OCC_SLACK = 64;           // floats of slack behind each staged plane / the column table
-constexpr int OCC_MIN_PART = 64;        // a tile's list is split over CTAs of at least this many splats
-constexpr int OCC_MAX_PARTS = 32;
-constexpr int OCC_RBOX_MAX = 60;        // largest window halo the tile kernel stages (2 planes <= ~190 KB)
-
-// Window halo (pixels) that covers the search disc of radius r (NDC) around any point of a tile, plus slack for
-// the rounding of floor() when the centre pixel is located.
-__host__ __device__ __forceinline__ int occ_halo(float r, int S) { return (int)ceilf(r * 0.5f * (float)S) + 2; }
-// Is view n handled by the tile kernel (window fits the staged box)?  Evaluated identically by both kernels.
-__host__ __device__ __forceinline__ bool occ_fits(float r, int S, int R_box) {
-    if (!(r >= 0.0f) || !(r < 4.0f) || R_box <= 0) return false;
-    return occ_halo(r, S) <= R_box;
-}
+constexpr int OCC_RBOX_MAX = 40;        // largest window halo the tile kernel stages (2 x 2 planes <= ~200 KB)
 
 __device__ __forceinline__ int centre_pixel(float p, int S) {
     return min(max((int)floorf((p + 1.0f) * (0.5f * (float)S)), 0), S - 1);
@@ -74,7 +65,8 @@ template <int PASS>
 __global__ void __launch_bounds__(256)
 occ_bin_kernel(const float4 *__restrict__ rec, const uint8_t *__restrict__ visible,
                const int64_t *__restrict__ first_idx, const int64_t *__restrict__ num_points, int64_t P0_shared,
-               int S, int OB, int32_t *__restrict__ counters, float4 *__restrict__ crec, int32_t *__restrict__ cids) {
+               int S, int OB, int32_t *__restrict__ counters, const int32_t *__restrict__ offsets,
+               float4 *__restrict__ crec, int32_t *__restrict__ cids) {
     extern __shared__ int32_t s_hist[];
     const int n = blockIdx.y;
     const int nt = OB * OB;
@@ -99,12 +91,14 @@ occ_bin_kernel(const float4 *__restrict__ rec, const uint8_t *__restrict__ visib
         }
     }
     __syncthreads();
+    // PASS 0 counts up; PASS 1 claims its range by counting the same counter back down to zero, so the counters are
+    // clean again for the next call (no memset, no cursor copy)
     int32_t *cnt = counters + (int64_t)n * nt;
     for (int t = threadIdx.x; t < nt; t += 256) {
         const int v = s_hist[t];
         if (v) {
-            const int base = atomicAdd(&cnt[t], v);
-            if (PASS == 1) s_hist[t] = base;
+            if (PASS == 0) atomicAdd(&cnt[t], v);
+            else s_hist[t] = offsets[(int64_t)n * nt + t] + atomicSub(&cnt[t], v) - v;
         }
     }
     if (PASS == 0) return;
@@ -343,197 +337,336 @@ __device__ __forceinline__ float rcp_approx(float x) {
     return y;
 }
 
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// 1.0f if a <= b else 0.0f (one FSET instruction); NaN -> 0
+__device__ __forceinline__ float set_le(float a, float b) {
+    float y;
+    asm("set.le.f32.f32 %0, %1, %2;" : "=f"(y) : "f"(a), "f"(b));
+    return y;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Work decomposition of the tile kernel.  A tile's list is cut into `parts` work items of <= OCC_ITEM splats
+// (occ_parts -> exclusive scan -> occ_items writes the tile of every item).  Items are handed to the persistent
+// CTAs in groups of OCC_GROUP consecutive items, round-robin, so that a CTA usually keeps the staged window for
+// a few items and every CTA sees a mix of views (their windows, hence costs, differ).
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ int occ_hh(float r, int S) {
+    // half-width H of the per-splat pixel window: pixel centres cx + 0.5 + k around a point at cx + f, f in [0,1),
+    // lie within r (pixels) only for |k| <= floor(r + 1/2); 1e-3 absorbs the rounding of floor() at pixel borders
+    return (int)floorf(r * 0.5f * (float)S + 0.5f + 1e-3f);
+}
+__host__ __device__ __forceinline__ bool occ_fits(float r, int S, int R_box) {
+    if (!(r >= 0.0f) || !(r < 4.0f) || R_box <= 0) return false;
+    return occ_hh(r, S) + 1 <= R_box;
+}
+
+__global__ void __launch_bounds__(256)
+occ_parts_kernel(const int32_t *__restrict__ tile_offsets, const float *__restrict__ rs, int nt_view, int64_t nt, int S,
+                 int R_box, int32_t *__restrict__ parts) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > nt) return;
+    int p = 0;
+    if (t < nt && occ_fits(rs[t / nt_view], S, R_box)) p = (tile_offsets[t + 1] - tile_offsets[t] + OCC_ITEM - 1) / OCC_ITEM;
+    parts[t] = p;   // parts[nt] = 0 so that the scan's last entry is the total
+}
+
+__global__ void __launch_bounds__(256)
+occ_items_kernel(const int32_t *__restrict__ part_off, int64_t nt, int32_t *__restrict__ item_tile) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nt) return;
+    for (int i = part_off[t]; i < part_off[t + 1]; ++i) item_tile[i] = (int32_t)t;
+}
+
 struct OccTileArgs {
     const float4 *crec;          // compact tile-ordered records {px, py, rx, ry}
     const int32_t *cids;         // packed splat id of every compact record
     const int32_t *tile_offsets; // (N*OB*OB + 1)
+    const int32_t *part_off;     // (N*OB*OB + 1) exclusive scan of the items per tile; last = number of items
+    const int32_t *item_tile;    // tile (n*OB*OB + tile) of every item
     const float *rs;             // (N,) search radius
     const float *planes;         // (N, 2, Hp, W)
     float2 *grad_xy;             // (P,) out
     int S, OB, R_box, side, W, Hp;
+    int lps8;                    // tuning: 8 lanes x 2 pairs instead of 4 lanes x 3..4 pairs for 17..32 columns
+    int64_t nt;
 };
 
-// Row walk of one column pair.  `off` = float index of (row j0, column sx) in the staged planes; yf2 holds the NDC y
-// of row j0 - 1 (POW2: advanced by exact additions of the pixel pitch, which are exact when S is a power of two --
-// every value is a multiple of 1/S below 2^24/S; otherwise the exact table s_yf is read).
-// CENTRE = rows that may contain the pixel under the point (d2 -> 0: clamp like the reference's eps_denom, 1e-10)
-// and the rows the splat's own bounding box can reach (positive gradients count there).
-template <bool CENTRE, bool POW2>
-__device__ __forceinline__ void occ_rows(int j0, int j1, const float *__restrict__ s_gm, const float *__restrict__ s_gp,
-                                         const float *__restrict__ s_yf_row0, int side, int off, float2 &yf2,
-                                         const float2 pix2, const float2 npy2, const float2 dxsq, const float ry,
-                                         const bool colin0, const bool colin1, const float r2, float2 &sw,
-                                         float2 &swy) {
-#pragma unroll 2
+// Everything the consumers need to know about a staged item (written by the producer warp)
+struct OccItem {
+    int cnt;        // splats in this item; < 0: no more work
+    int beg;        // first compact record
+    int wbuf;       // which window buffer holds the tile's planes
+    int tx, ty;     // tile coordinates
+    int hh;         // window half-width of the view
+    float r2;       // squared search radius
+    int pad;
+};
+
+// Row walk for one batch of splats.  A lane owns PPL pairs of adjacent window columns of its splat (pair s = columns
+// 2*(s*LPS + gl) + {0,1}); all lanes walk the rows j0..j1 together.  Per pair and row: one LDS.64, d2 for both
+// columns with one packed FMA, ONE reciprocal for both (1/(a*b), then *b and *a), the disc test as a 0/1 factor,
+// two packed accumulations:  sw += w,  swy += w*dy  (the x half is factored: sum_rows dx*w = dx * sum_rows w).
+// CENTRE rows (those the splat's own bbox can reach) additionally clamp d2 at 1e-10 (the pixel under the point,
+// rasterization_utils.cuh:37-43) and add the positive gradients inside the bbox
+// (rasterize_points_backward.cu:161-168) as g+ * colmask * rowmask.
+template <int LPS, int PPL, bool CENTRE, bool POW2>
+__device__ __forceinline__ void occ_rows(int j0, int j1, const float *__restrict__ gm, const float *__restrict__ gp,
+                                         const float *__restrict__ yf_tab, const int side, float2 &yf2,
+                                         const float2 pix2, const float2 npy2, const float ry, const float r2,
+                                         const float2 (&dxsq)[PPL], const float2 (&cmask)[PPL], float2 (&sw)[PPL],
+                                         float2 (&swy)[PPL]) {
+    gm += j0 * side;
+    gp += j0 * side;
     for (int j = j0; j < j1; ++j) {
-        float2 g = *reinterpret_cast<const float2 *>(s_gm + off);
         if (POW2) {
-            yf2 = __fadd2_rn(yf2, pix2);
+            yf2 = __fadd2_rn(yf2, pix2);          // exact: multiples of 1/S (see occ_tile_kernel)
         } else {
-            const float yf = s_yf_row0[j];
+            const float yf = yf_tab[j];
             yf2 = make_float2(yf, yf);
         }
         const float2 dy2 = __fadd2_rn(yf2, npy2);
-        const float2 d2 = __ffma2_rn(dy2, dy2, dxsq);          // dy*dy + dx*dx, two columns at once
-        const bool out0 = d2.x > r2, out1 = d2.y > r2;         // rasterize_points_backward.cu:156
-        float2 inv;
+        float2 rowm2 = make_float2(0.f, 0.f);
         if (CENTRE) {
-            inv.x = rcp_approx(fmaxf(d2.x, 1e-10f));           // rasterization_utils.cuh:37-43 (d2 >= 0)
-            inv.y = rcp_approx(fmaxf(d2.y, 1e-10f));
-            // positive gradients only inside the splat's bounding box: rasterize_points_backward.cu:161-168
-            const float2 gp = *reinterpret_cast<const float2 *>(s_gp + off);
-            const bool rowin = !(fabsf(dy2.x) > ry);
-            g.x += (rowin && colin0) ? gp.x : 0.0f;            // g- and g+ are never both non-zero: exact
-            g.y += (rowin && colin1) ? gp.y : 0.0f;
-        } else {
-            inv.x = rcp_approx(d2.x);                          // >= one pixel away from the point: d2 >> 1e-10
-            inv.y = rcp_approx(d2.y);
+            const float m = set_le(fabsf(dy2.x), ry);
+            rowm2 = make_float2(m, m);
         }
-        float2 w = __fmul2_rn(g, inv);                         // g / max(d2, 1e-10)   (:170-172)
-        w.x = out0 ? 0.0f : w.x;
-        w.y = out1 ? 0.0f : w.y;
-        sw = __fadd2_rn(sw, w);
-        swy = __ffma2_rn(w, dy2, swy);
-        off += side;
+#pragma unroll
+        for (int s = 0; s < PPL; ++s) {
+            float2 g = *reinterpret_cast<const float2 *>(gm + s * 2 * LPS);
+            const float2 d2 = __ffma2_rn(dy2, dy2, dxsq[s]);                    // dy*dy + dx*dx
+            const float2 in = make_float2(set_le(d2.x, r2), set_le(d2.y, r2));   // rasterize_points_backward.cu:156
+            float2 dc = d2;
+            if (CENTRE) {
+                dc.x = fmaxf(d2.x, 1e-10f);
+                dc.y = fmaxf(d2.y, 1e-10f);
+                const float2 gpv = *reinterpret_cast<const float2 *>(gp + s * 2 * LPS);
+                g = __ffma2_rn(gpv, __fmul2_rn(cmask[s], rowm2), g);            // g- and g+ never both non-zero
+            }
+            const float ip = rcp_approx(dc.x * dc.y);
+            const float2 inv = make_float2(ip * dc.y, ip * dc.x);                // 1/dc.x, 1/dc.y
+            const float2 w = __fmul2_rn(__fmul2_rn(g, inv), in);                 // g / max(d2, 1e-10) inside the disc
+            sw[s] = __fadd2_rn(sw[s], w);
+            swy[s] = __ffma2_rn(w, dy2, swy[s]);
+        }
+        gm += side;
+        gp += side;
     }
 }
 
-template <bool POW2>
-__global__ void __launch_bounds__(OCC_THREADS)
-occ_tile_kernel(const __grid_constant__ OccTileArgs a) {
-    extern __shared__ __align__(128) unsigned char occ_smem[];
-    const int n = blockIdx.y, tile = blockIdx.x;
-    const int S = a.S, OB = a.OB, side = a.side, R_box = a.R_box;
-    const float r = a.rs[n];
-    if (!occ_fits(r, S, R_box)) return;          // this view is handled by occ_generic_kernel
-    const int64_t tb = (int64_t)n * OB * OB + tile;
-    int beg = a.tile_offsets[tb], end = a.tile_offsets[tb + 1];
-    if (beg == end) return;
-    {
-        // a tile's list is split over up to gridDim.z CTAs so that dense tiles do not serialise on one CTA;
-        // every CTA stages the (small, L2-resident) window itself
-        const int count = end - beg;
-        const int parts = min((int)gridDim.z, (count + OCC_MIN_PART - 1) / OCC_MIN_PART);
-        if ((int)blockIdx.z >= parts) return;
-        const int per = (count + parts - 1) / parts;
-        beg += (int)blockIdx.z * per;
-        end = min(end, beg + per);
-        if (beg >= end) return;
-    }
-    const int plane_elems = side * side + OCC_SLACK;
-    float *s_gm = reinterpret_cast<float *>(occ_smem);
-    float *s_gp = s_gm + plane_elems;
-    float *s_xf = s_gp + plane_elems;                     // side + OCC_SLACK column centres (NDC)
-    float *s_yf = s_xf + side + OCC_SLACK;                // side row centres
-    float4 *s_rec = reinterpret_cast<float4 *>(s_yf + side);
-    unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(s_rec + OCC_RCAP);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int ty = tile / OB, tx = tile - ty * OB;
-    const int wx0 = tx * OCC_TILE - R_box, wy0 = ty * OCC_TILE - R_box;   // window origin (NDC-index pixels)
-    const uint32_t bar = smem_u32(s_bar);
-
-    if (tid == 0) {
-        mbar_init(bar, 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
-    int cnt = min(OCC_RCAP, end - beg);
-    if (warp == 0) {
-        // TMA stage: 2*side row copies (window of both planes; plane padding == R_box so the window origin is
-        // (ty*32, tx*32) in plane coordinates and every row is 16-byte aligned) + this CTA's first record chunk
-        if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)(2 * side * side * 4 + cnt * 16));
-        __syncwarp();
-        const float *src0 = a.planes + (((int64_t)n * 2) * a.Hp + (int64_t)ty * OCC_TILE) * a.W + tx * OCC_TILE;
-        for (int row = lane; row < 2 * side; row += 32) {
-            const int pl = row >= side ? 1 : 0, rr = row - pl * side;
-            const float *src = src0 + ((int64_t)pl * a.Hp + rr) * a.W;
-            bulk_copy_g2s(smem_u32((pl ? s_gp : s_gm) + rr * side), src, (uint32_t)(side * 4), bar);
-        }
-        if (lane == 0) bulk_copy_g2s(smem_u32(s_rec), a.crec + beg, (uint32_t)(cnt * 16), bar);
-    }
-    // exact pixel-centre NDC coordinates of the window's columns / rows (the reference's PixToNdc, division
-    // included, evaluated once per CTA instead of once per pair)
-    for (int i = tid; i < side + OCC_SLACK; i += OCC_THREADS) {
-        s_xf[i] = pix_to_ndc(wx0 + i, S);
-        if (i < side) s_yf[i] = pix_to_ndc(wy0 + i, S);
-    }
-    __syncthreads();
-
-    const int R = occ_halo(r, S);
-    const int Rw = R - 1;                        // per-splat window half-width in pixels (covers the disc)
-    const int Wwin = 2 * Rw + 1;
-    const int need = Wwin + 1;                   // + 1: the window is shifted left to an even column
-    int lps = 4;                                 // lanes per splat; each lane owns two adjacent columns
-    while (2 * lps < need && lps < 32) lps <<= 1;
-    const int ncb = (need + 2 * lps - 1) / (2 * lps);    // column blocks (1 unless the window is > 64 wide)
-    const int groups = 32 / lps;
-    const int grp = lane / lps, gl = lane - grp * lps;
-    const float r2 = r * r;
+// One staged item: `cnt` splats of one tile.  Warp w takes batches w, w + 8, ...; a batch is 32 / LPS splats.
+template <int LPS, int PPL, bool POW2>
+__device__ __forceinline__ void occ_item(const OccTileArgs &a, const OccItem &it, const float *__restrict__ s_gm,
+                                         const float *__restrict__ s_gp, const float *__restrict__ s_xf,
+                                         const float *__restrict__ s_yf, const float4 *__restrict__ s_rec, int warp,
+                                         int lane) {
+    constexpr int GROUPS = 32 / LPS;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int S = a.S, side = a.side;
+    const int grp = lane / LPS, gl = lane - grp * LPS;
+    const int Hh = it.hh, Wwin = 2 * Hh + 1;
+    const int wx0 = it.tx * OCC_TILE - a.R_box, wy0 = it.ty * OCC_TILE - a.R_box;
     const float half_S = 0.5f * (float)S;
     const float pixf = 2.0f / (float)S;
     const float2 pix2 = make_float2(pixf, pixf);
-    constexpr unsigned FULL = 0xffffffffu;
-    constexpr int NW = OCC_THREADS / 32;
-
-    uint32_t phase = 0;
-    for (int cbase = beg; cbase < end; cbase += OCC_RCAP) {
-        if (cbase > beg) {
-            // next record chunk: everyone is done with the previous one, re-arm the barrier and let the TMA refill
-            __syncthreads();
-            cnt = min(OCC_RCAP, end - cbase);
-            if (tid == 0) {
-                mbar_arrive_expect_tx(bar, (uint32_t)(cnt * 16));
-                bulk_copy_g2s(smem_u32(s_rec), a.crec + cbase, (uint32_t)(cnt * 16), bar);
-            }
+    const float r2 = it.r2;
+    for (int b = warp; b * GROUPS < it.cnt; b += OCC_CONSUMERS) {
+        const int k = b * GROUPS + grp;
+        const bool have = k < it.cnt;
+        const float4 rc = s_rec[have ? k : 0];
+        const float px = rc.x, py = rc.y, rx = rc.z, ry = rc.w;
+        // the id is only needed for the final store: issue the load now so that its latency hides behind the rows
+        const int id = (have && gl == 0) ? __ldg(&a.cids[it.beg + k]) : 0;
+        // centre pixel (this tile's by construction; the clamp only absorbs points outside the image) and the
+        // window origin in staged coordinates, shifted left to an even column (8-byte aligned LDS.64)
+        const int cx = min(max(centre_pixel(px, S), it.tx * OCC_TILE), it.tx * OCC_TILE + OCC_TILE - 1);
+        const int cy = min(max(centre_pixel(py, S), it.ty * OCC_TILE), it.ty * OCC_TILE + OCC_TILE - 1);
+        const int ox = (cx - Hh - wx0) & ~1, oy = cy - Hh - wy0;
+        // rows the splat's own bbox can reach (+1 for rounding), at least the 3 rows around the point
+        int bh = have ? min(Hh, (int)fminf(ceilf(ry * half_S) + 1.0f, 4096.0f)) : 0;
+        bh = max(__reduce_max_sync(FULL, bh), min(Hh, 1));
+        const int jc0 = Hh - bh, jc1 = Hh + bh + 1;
+        const float2 npy2 = make_float2(-py, -py);
+        float2 dxsq[PPL], cmask[PPL], sw[PPL], swy[PPL];
+        const float *xfp = s_xf + ox + 2 * gl;
+#pragma unroll
+        for (int s = 0; s < PPL; ++s) {
+            const float2 xf = *reinterpret_cast<const float2 *>(xfp + s * 2 * LPS);
+            const float dx0 = xf.x - px, dx1 = xf.y - px;
+            dxsq[s] = make_float2(dx0 * dx0, dx1 * dx1);
+            cmask[s] = make_float2(set_le(fabsf(dx0), rx), set_le(fabsf(dx1), rx));
+            sw[s] = make_float2(0.f, 0.f);
+            swy[s] = make_float2(0.f, 0.f);
         }
-        mbar_wait(bar, phase);
-        phase ^= 1u;
-
-        for (int k0 = warp * groups; k0 < cnt; k0 += NW * groups) {
-            const int k = k0 + grp;
-            const bool have = k < cnt;
-            const float4 rc = s_rec[have ? k : 0];
-            const float px = rc.x, py = rc.y, rx = rc.z, ry = rc.w;
-            // centre pixel, clamped into this tile (it is this tile's by construction; the clamp only absorbs
-            // rounding), and the window origin in staged coordinates (always inside: R_box >= R = Rw + 1)
-            const int cx = min(max(centre_pixel(px, S), tx * OCC_TILE), tx * OCC_TILE + OCC_TILE - 1);
-            const int cy = min(max(centre_pixel(py, S), ty * OCC_TILE), ty * OCC_TILE + OCC_TILE - 1);
-            const int ox = (cx - Rw - wx0) & ~1, oy = cy - Rw - wy0;
-            // rows the splat's own bbox can reach (+1 for rounding) -- at least the 3 rows around the point
-            int bh = have ? min(Rw, (int)fminf(ceilf(ry * half_S) + 1.0f, 4096.0f)) : 0;
-            bh = max(__reduce_max_sync(FULL, bh), min(Rw, 1));
-            const int jc0 = Rw - bh, jc1 = Rw + bh + 1;
-            const float2 npy2 = make_float2(-py, -py);
-            float gx = 0.f, gy = 0.f;
-            for (int cb = 0; cb < ncb; ++cb) {
-                const int sx = ox + cb * 2 * lps + 2 * gl;                  // even
-                const float2 xf = *reinterpret_cast<const float2 *>(s_xf + sx);
-                const float dx0 = xf.x - px, dx1 = xf.y - px;
-                const float2 dxsq = make_float2(dx0 * dx0, dx1 * dx1);
-                const bool colin0 = !(fabsf(dx0) > rx), colin1 = !(fabsf(dx1) > rx);
-                float2 sw = make_float2(0.f, 0.f), swy = make_float2(0.f, 0.f);
-                const float yfm1 = s_yf[oy] - pixf;                        // row -1 (POW2: exact)
-                float2 yf2 = make_float2(yfm1, yfm1);
-                const int off = oy * side + sx;
-                occ_rows<false, POW2>(0, jc0, s_gm, s_gp, s_yf + oy, side, off, yf2, pix2, npy2, dxsq, ry, colin0, colin1,
-                                      r2, sw, swy);
-                occ_rows<true, POW2>(jc0, jc1, s_gm, s_gp, s_yf + oy, side, off + jc0 * side, yf2, pix2, npy2, dxsq, ry,
-                                     colin0, colin1, r2, sw, swy);
-                occ_rows<false, POW2>(jc1, Wwin, s_gm, s_gp, s_yf + oy, side, off + jc1 * side, yf2, pix2, npy2, dxsq, ry,
-                                      colin0, colin1, r2, sw, swy);
-                gx = fmaf(dx0, sw.x, fmaf(dx1, sw.y, gx));                 // sum_rows dx*w = dx * sum_rows w
-                gy += swy.x + swy.y;
-            }
-            for (int d = lps >> 1; d > 0; d >>= 1) {
-                gx += __shfl_xor_sync(FULL, gx, d);
-                gy += __shfl_xor_sync(FULL, gy, d);
-            }
-            // rasterize_points_backward.cu:145 -- points outside the renderable area get no gradient
-            if (have && gl == 0 && !(fabsf(py) > 1.0f || fabsf(px) > 1.0f))
-                a.grad_xy[a.cids[cbase + k]] = make_float2(gx, gy);
+        const float yfm1 = s_yf[oy] - pixf;                  // row -1 (POW2: exact)
+        float2 yf2 = make_float2(yfm1, yfm1);
+        const int off = oy * side + ox + 2 * gl;
+        occ_rows<LPS, PPL, false, POW2>(0, jc0, s_gm + off, s_gp + off, s_yf + oy, side, yf2, pix2, npy2, ry, r2, dxsq, cmask,
+                                        sw, swy);
+        occ_rows<LPS, PPL, true, POW2>(jc0, jc1, s_gm + off, s_gp + off, s_yf + oy, side, yf2, pix2, npy2, ry, r2, dxsq, cmask,
+                                       sw, swy);
+        occ_rows<LPS, PPL, false, POW2>(jc1, Wwin, s_gm + off, s_gp + off, s_yf + oy, side, yf2, pix2, npy2, ry, r2, dxsq, cmask,
+                                        sw, swy);
+        float gx = 0.f, gy = 0.f;
+#pragma unroll
+        for (int s = 0; s < PPL; ++s) {
+            const float2 xf = *reinterpret_cast<const float2 *>(xfp + s * 2 * LPS);
+            gx = fmaf(xf.x - px, sw[s].x, fmaf(xf.y - px, sw[s].y, gx));   // sum_rows dx*w = dx * sum_rows w
+            gy += swy[s].x + swy[s].y;
         }
+#pragma unroll
+        for (int d = LPS >> 1; d > 0; d >>= 1) {
+            gx += __shfl_xor_sync(FULL, gx, d);
+            gy += __shfl_xor_sync(FULL, gy, d);
+        }
+        // rasterize_points_backward.cu:145 -- points outside the renderable area get no gradient
+        if (have && gl == 0 && !(fabsf(py) > 1.0f || fabsf(px) > 1.0f)) a.grad_xy[id] = make_float2(gx, gy);
     }
 }
+
+// Persistent, warp-specialised: warp 8 is the PRODUCER -- it decodes the next work item, computes the window's
+// pixel-centre tables and drives the TMA engine (cp.async.bulk row copies of both gradient planes into the free
+// window buffer when the tile changes, the item's records into the free record buffer), completion signalled on the
+// slot's "full" mbarrier; warps 0-7 are CONSUMERS -- they wait on "full", gather, and release the slot through its
+// "empty" mbarrier.  Two item slots and two window buffers are in flight, so staging overlaps the arithmetic.
+template <bool POW2>
+__global__ void __launch_bounds__(OCC_THREADS, 2)
+occ_tile_kernel(const __grid_constant__ OccTileArgs a) {
+    extern __shared__ __align__(128) unsigned char occ_smem[];
+    const int S = a.S, OB = a.OB, side = a.side, R_box = a.R_box;
+    const int plane_elems = side * side + OCC_SLACK;
+    const int win_elems = 2 * plane_elems + 2 * side + OCC_SLACK;   // g-, g+, column table (+slack), row table
+    float *s_win = reinterpret_cast<float *>(occ_smem);              // 2 window buffers
+    float4 *s_rec = reinterpret_cast<float4 *>(s_win + 2 * win_elems);               // 2 x OCC_ITEM records
+    OccItem *s_item = reinterpret_cast<OccItem *>(s_rec + 2 * OCC_ITEM);              // 2 item descriptors
+    unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(s_item + 2);  // full[2], empty[2]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t bar_full = smem_u32(s_bar), bar_empty = smem_u32(s_bar + 2);
+
+    if (tid == 0) {
+        mbar_init(bar_full, 1);
+        mbar_init(bar_full + 8, 1);
+        mbar_init(bar_empty, OCC_CONSUMERS);
+        mbar_init(bar_empty + 8, OCC_CONSUMERS);
+        mbar_fence_init();
+    }
+    // the slack behind the planes / column table is read (and masked out) by lanes whose column pairs lie beyond
+    // the window: keep it finite
+    for (int i = tid; i < 2 * 3 * OCC_SLACK; i += OCC_THREADS) {
+        const int wb = i / (3 * OCC_SLACK), q = (i / OCC_SLACK) % 3, e = i % OCC_SLACK;
+        float *w = s_win + wb * win_elems;
+        (q == 0 ? w + side * side : q == 1 ? w + plane_elems + side * side : w + 2 * plane_elems + side)[e] = 0.0f;
+    }
+    __syncthreads();
+
+    const int n_items = a.part_off[a.nt];
+    const int n_groups = (n_items + OCC_GROUP - 1) / OCC_GROUP;
+    const int my_groups = ((int)blockIdx.x < n_groups) ? (n_groups - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    // sequence number q of this CTA's items: group = blockIdx.x + (q / OCC_GROUP) * gridDim.x, item = group*G + q%G
+    const int q_end = my_groups * OCC_GROUP;
+
+    if (warp == OCC_CONSUMERS) {
+        // ------------------------------- producer -------------------------------
+        int wt_cur = -1;                       // tile held by the current window buffer
+        int wcur = 0;
+        int slot_use = 0;                      // items staged so far
+        for (int q = 0; q <= q_end; ++q) {
+            const int slot = slot_use & 1;
+            int item = -1;
+            if (q < q_end) {
+                item = ((int)blockIdx.x + (q / OCC_GROUP) * (int)gridDim.x) * OCC_GROUP + (q % OCC_GROUP);
+                if (item >= n_items) continue;
+            }
+            // wait until the consumers have released this slot (its previous use)
+            if (slot_use >= 2) mbar_wait(bar_empty + 8 * slot, (uint32_t)(((slot_use >> 1) - 1) & 1));
+            OccItem *it = s_item + slot;
+            if (item < 0) {
+                if (lane == 0) {
+                    it->cnt = -1;
+                    mbar_arrive(bar_full + 8 * slot);
+                }
+                break;
+            }
+            const int t = a.item_tile[item];
+            const int n = t / (OB * OB), tile = t - n * OB * OB;
+            const int ty = tile / OB, tx = tile - ty * OB;
+            const int p = item - a.part_off[t], parts = a.part_off[t + 1] - a.part_off[t];
+            const int tb = a.tile_offsets[t], count = a.tile_offsets[t + 1] - tb;
+            const int per = (count + parts - 1) / parts;
+            const int beg = tb + p * per;
+            const int cnt = max(0, min(count - p * per, per));
+            const float r = a.rs[n];
+            const bool load_win = wt_cur != t;
+            if (load_win) {
+                // the other buffer was last used by items <= (this item - 2) of an earlier tile: already released
+                if (wt_cur >= 0) wcur ^= 1;
+                wt_cur = t;
+            }
+            float *w = s_win + wcur * win_elems;
+            if (load_win) {
+                // exact pixel-centre NDC coordinates of the window's columns / rows (the reference's PixToNdc,
+                // division included, once per tile instead of once per pair).  Written before the arrive below so
+                // that its release (after __syncwarp) publishes them to the consumers together with the descriptor.
+                float *xf = w + 2 * plane_elems, *yf = xf + side + OCC_SLACK;
+                const int wx0 = tx * OCC_TILE - R_box, wy0 = ty * OCC_TILE - R_box;
+                for (int i = lane; i < side + OCC_SLACK; i += 32) {
+                    xf[i] = pix_to_ndc(wx0 + i, S);
+                    if (i < side) yf[i] = pix_to_ndc(wy0 + i, S);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                it->cnt = cnt;
+                it->beg = beg;
+                it->wbuf = wcur;
+                it->tx = tx;
+                it->ty = ty;
+                it->hh = occ_hh(r, S);
+                it->r2 = r * r;
+                mbar_arrive_expect_tx(bar_full + 8 * slot, (uint32_t)((load_win ? 2 * side * side * 4 : 0) + cnt * 16));
+            }
+            __syncwarp();
+            if (load_win) {
+                // plane padding == R_box, so the window origin is (ty*32, tx*32) in plane coordinates and every row
+                // copy is 16-byte aligned on both sides
+                const float *src0 = a.planes + (((int64_t)n * 2) * a.Hp + (int64_t)ty * OCC_TILE) * a.W + tx * OCC_TILE;
+                for (int row = lane; row < 2 * side; row += 32) {
+                    const int pl = row >= side ? 1 : 0, rr = row - pl * side;
+                    bulk_copy_g2s(smem_u32(w + pl * plane_elems + rr * side), src0 + ((int64_t)pl * a.Hp + rr) * a.W,
+                                  (uint32_t)(side * 4), bar_full + 8 * slot);
+                }
+            }
+            if (lane == 0 && cnt > 0)
+                bulk_copy_g2s(smem_u32(s_rec + slot * OCC_ITEM), a.crec + beg, (uint32_t)(cnt * 16), bar_full + 8 * slot);
+            ++slot_use;
+        }
+        return;
+    }
+    // --------------------------------- consumers ---------------------------------
+    for (int use = 0;; ++use) {
+        const int slot = use & 1;
+        mbar_wait(bar_full + 8 * slot, (uint32_t)((use >> 1) & 1));
+        const OccItem it = s_item[slot];
+        if (it.cnt < 0) break;
+        const float *w = s_win + it.wbuf * win_elems;
+        const float *s_gm = w, *s_gp = w + plane_elems, *s_xf = w + 2 * plane_elems, *s_yf = s_xf + side + OCC_SLACK;
+        const float4 *rec = s_rec + slot * OCC_ITEM;
+        const int need = 2 * it.hh + 2;          // window columns + 1 for the shift to an even column
+        if (need <= 8) occ_item<4, 1, POW2>(a, it, s_gm, s_gp, s_xf, s_yf, rec, warp, lane);
+        else if (need <= 16) occ_item<4, 2, POW2>(a, it, s_gm, s_gp, s_xf, s_yf, rec, warp, lane);
+        else if (need <= 32 && a.lps8) occ_item<8, 2, POW2>(a, it, s_gm, s_gp, s_xf, s_yf, rec, warp, lane);
+        else if (need <= 24) occ_item<4, 3, POW2>(a, it, s_gm, s_gp, s_xf, s_yf, rec, warp, lane);
+        else if (need <= 32) occ_item<4, 4, POW2>(a, it, s_gm, s_gp, s_xf, s_yf, rec, warp, lane);
+        else if (need <= 48) occ_item<8, 3, POW2>(a, it, s_gm, s_gp, s_xf, s_yf, rec, warp, lane);
+        else if (need <= 64) occ_item<8, 4, POW2>(a, it, s_gm, s_gp, s_xf, s_yf, rec, warp, lane);
+        else occ_item<16, 3, POW2>(a, it, s_gm, s_gp, s_xf, s_yf, rec, warp, lane);   // need <= 96 (R_box <= 40)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty + 8 * slot);
+    }
+}
+
 
 // ---------------------------------------------------------------------------------------------
 // Generic gather for views whose window does not fit the staged box (very large search radius): one warp per
@@ -652,12 +785,13 @@ int occ_backward(dss_ctx *ctx, const float4 *rec, const uint8_t *visible, float 
     float hint = 0.0f;
     for (int i = 0; i < (N < 96 ? N : 96); ++i) hint = fmaxf(hint, h_rs[i]);
     int R_box = 20;
-    if (hint > 0.0f && hint < 4.0f) R_box = (occ_halo(hint * 1.15f, S) + 1 + 3) & ~3;
+    if (hint > 0.0f && hint < 4.0f) R_box = (occ_hh(hint * 1.15f, S) + 2 + 3) & ~3;
     if (R_box < 8) R_box = 8;
     if (R_box > OCC_RBOX_MAX) R_box = OCC_RBOX_MAX;
     const int side = OCC_TILE + 2 * R_box;
-    const size_t smem = (size_t)(2 * (side * side + OCC_SLACK) + 2 * side + OCC_SLACK) * sizeof(float) +
-                        (size_t)OCC_RCAP * sizeof(float4) + 16;
+    const size_t win_elems = (size_t)2 * (side * side + OCC_SLACK) + 2 * side + OCC_SLACK;
+    const size_t smem = 2 * win_elems * sizeof(float) + 2 * (size_t)OCC_ITEM * sizeof(float4) + 2 * sizeof(OccItem) +
+                        4 * sizeof(unsigned long long);
     const bool tiles_ok = (size_t)OB * OB * sizeof(int32_t) <= 200 * 1024 && nt + 1 < (int64_t)INT32_MAX &&
                           Ptot < (int64_t)INT32_MAX;
     if (!tiles_ok) R_box = 0;
@@ -668,26 +802,32 @@ int occ_backward(dss_ctx *ctx, const float4 *rec, const uint8_t *visible, float 
         float4 *crec = nullptr;
         float *planes = nullptr;
         const int PAD = R_box, W = OB * OCC_TILE + 2 * PAD, Hp = W;
-        if ((rc = ctx_get(ctx, BUF_TILE_COUNTS, (size_t)(nt + 1), &counts))) return rc;
+        if ((rc = ctx_get(ctx, BUF_OCC_COUNTS, (size_t)(nt + 1), &counts))) return rc;
         if ((rc = ctx_get(ctx, BUF_TILE_OFFSETS, (size_t)(nt + 1), &offsets))) return rc;
-        if ((rc = ctx_get(ctx, BUF_TILE_IDS, (size_t)(Ptot > 0 ? Ptot : 1), &cids))) return rc;
+        if ((rc = ctx_get(ctx, BUF_OCC_IDS, (size_t)(Ptot > 0 ? Ptot : 1), &cids))) return rc;
         if ((rc = ctx_get(ctx, BUF_OCC_REC, (size_t)(Ptot > 0 ? Ptot : 1), &crec))) return rc;
         if ((rc = ctx_get(ctx, BUF_OCC_PLANES, (size_t)N * 2 * Hp * W, &planes))) return rc;
         {
             StageScope prof(ctx, ST_OCC_BIN, st);
-            DSS_CUDA_TRY(cudaMemsetAsync(counts, 0, (size_t)(nt + 1) * sizeof(int32_t), st));
+            // the per-tile counters live in their own buffer and are left at zero by every successful call
+            const bool clean = ctx->occ_counts_ptr == counts && ctx->occ_counts_elems >= (size_t)(nt + 1);
+            ctx->occ_counts_ptr = nullptr;   // restored below; an error in between forces the memset next time
+            if (!clean) DSS_CUDA_TRY(cudaMemsetAsync(counts, 0, ctx->cap[BUF_OCC_COUNTS], st));
             dim3 bgrid((unsigned)((P0 + 2047) / 2048), N);
             const size_t hist = (size_t)OB * OB * sizeof(int32_t);
             if (hist > 48 * 1024) {
                 DSS_CUDA_TRY(cudaFuncSetAttribute(occ_bin_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist));
                 DSS_CUDA_TRY(cudaFuncSetAttribute(occ_bin_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist));
             }
-            occ_bin_kernel<0><<<bgrid, 256, hist, st>>>(rec, visible, first_idx, num_points, P0, S, OB, counts, nullptr, nullptr);
+            occ_bin_kernel<0><<<bgrid, 256, hist, st>>>(rec, visible, first_idx, num_points, P0, S, OB, counts, nullptr, nullptr,
+                                                        nullptr);
             DSS_LAUNCH_CHECK(ctx);
             if ((rc = exclusive_scan_i32(ctx, counts, offsets, nt + 1, st))) return rc;
-            DSS_CUDA_TRY(cudaMemcpyAsync(counts, offsets, (size_t)nt * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
-            occ_bin_kernel<1><<<bgrid, 256, hist, st>>>(rec, visible, first_idx, num_points, P0, S, OB, counts, crec, cids);
+            occ_bin_kernel<1><<<bgrid, 256, hist, st>>>(rec, visible, first_idx, num_points, P0, S, OB, counts, offsets, crec,
+                                                        cids);
             DSS_LAUNCH_CHECK(ctx);
+            ctx->occ_counts_ptr = counts;
+            ctx->occ_counts_elems = ctx->cap[BUF_OCC_COUNTS] / sizeof(int32_t);
         }
         if (compute_rs) {
             unsigned int *hist = nullptr;
@@ -708,10 +848,23 @@ int occ_backward(dss_ctx *ctx, const float4 *rec, const uint8_t *visible, float 
             occ_planes_kernel<<<pgrid, 256, 0, st>>>(grad_occ, pix_stride, pix_offset, S, PAD, W, Hp, planes);
             DSS_LAUNCH_CHECK(ctx);
         }
+        // work items: parts per tile -> scan -> tile of every item
+        int32_t *parts = nullptr, *item_tile = nullptr;
+        const int64_t max_items = Ptot / OCC_ITEM + nt + 1;
+        if ((rc = ctx_get(ctx, BUF_OCC_PARTS, (size_t)(2 * (nt + 1)), &parts))) return rc;
+        if ((rc = ctx_get(ctx, BUF_OCC_ITEMS, (size_t)max_items, &item_tile))) return rc;
+        int32_t *part_off = parts + (nt + 1);
+        occ_parts_kernel<<<(unsigned)((nt + 1 + 255) / 256), 256, 0, st>>>(offsets, rs, OB * OB, nt, S, R_box, parts);
+        DSS_LAUNCH_CHECK(ctx);
+        if ((rc = exclusive_scan_i32(ctx, parts, part_off, nt + 1, st))) return rc;
+        occ_items_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(part_off, nt, item_tile);
+        DSS_LAUNCH_CHECK(ctx);
         OccTileArgs a;
         a.crec = crec;
         a.cids = cids;
         a.tile_offsets = offsets;
+        a.part_off = part_off;
+        a.item_tile = item_tile;
         a.rs = rs;
         a.planes = planes;
         a.grad_xy = reinterpret_cast<float2 *>(grad_xy);
@@ -721,8 +874,16 @@ int occ_backward(dss_ctx *ctx, const float4 *rec, const uint8_t *visible, float 
         a.side = side;
         a.W = W;
         a.Hp = Hp;
+        a.nt = nt;
+        a.lps8 = ctx->occ_lps8;
         const bool pow2 = (S & (S - 1)) == 0;
-        dim3 tgrid((unsigned)(OB * OB), N, OCC_MAX_PARTS);
+        // persistent: as many CTAs as fit (2 per SM at the usual window sizes), items round-robin in groups
+        int per_sm = (int)((size_t)220 * 1024 / (smem + 1024));
+        if (per_sm > 2) per_sm = 2;
+        if (per_sm < 1) per_sm = 1;
+        int64_t want = (max_items + OCC_GROUP - 1) / OCC_GROUP;
+        unsigned tgrid = (unsigned)(want < (int64_t)ctx->sm_count * per_sm ? want : (int64_t)ctx->sm_count * per_sm);
+        if (tgrid < 1) tgrid = 1;
         if (pow2) {
             DSS_CUDA_TRY(cudaFuncSetAttribute(occ_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             occ_tile_kernel<true><<<tgrid, OCC_THREADS, smem, st>>>(a);
@@ -737,7 +898,7 @@ int occ_backward(dss_ctx *ctx, const float4 *rec, const uint8_t *visible, float 
     {
         // views whose window does not fit (very large search radius) take the direct global-memory gather
         StageScope prof(ctx, ST_OCC_BWD, st);
-        dim3 grid(occ_nblocks(P0, OCC_WARPS * 32, ctx->sm_count, 64), N);
+        dim3 grid(occ_nblocks(P0, OCC_WARPS * 32, ctx->sm_count, 4), N);   // grid-stride; usually every block returns at once
         occ_generic_kernel<<<grid, OCC_WARPS * 32, 0, st>>>(rec, visible, rs, grad_occ, pix_stride, pix_offset, first_idx,
                                                             num_points, P0, S, R_box,
                                                             reinterpret_cast<float2 *>(grad_xy));

@@ -68,7 +68,7 @@ raster_fwd_kernel(const __grid_constant__ RasterArgs a) {
     float thresh = CUDART_INF_F;  // warp-wide max of the KMAX-th nearest depth
 
     const int64_t tbase = ((int64_t)n * B * B + tile) * a.NS;
-    const int beg = a.tile_offsets[tbase], end = a.tile_offsets[tbase + a.NS];
+    const int beg = min(a.tile_offsets[tbase], a.ids_capacity), end = min(a.tile_offsets[tbase + a.NS], a.ids_capacity);
 
     for (int base = beg; base < end; base += RASTER_CHUNK) {
         const int cnt = min(RASTER_CHUNK, end - base);
@@ -163,7 +163,7 @@ raster_fwd_kernel(const __grid_constant__ RasterArgs a) {
             if (emit[k]) {
                 const int id = fid[k];
                 w[k] = expf(-0.5f * fq[k]) * __ldg(&a.scaler[id]);
-                const float *c = a.colours + (int64_t)id * 3;
+                const float *c = a.colours + ((int64_t)id - (int64_t)n * a.colour_P0) * 3;
                 r += w[k] * __ldg(c + 0);
                 g += w[k] * __ldg(c + 1);
                 b += w[k] * __ldg(c + 2);
@@ -267,7 +267,7 @@ __device__ __forceinline__ void raster_epilogue(const RasterArgs &a, const unsig
             if (emit[k]) {
                 const int id = fid[k];
                 w[k] = expf(-0.5f * fq[k]) * __ldg(&a.scaler[id]);
-                const float *c = a.colours + (int64_t)id * 3;
+                const float *c = a.colours + ((int64_t)id - (int64_t)n * a.colour_P0) * 3;
                 r += w[k] * __ldg(c + 0);
                 g += w[k] * __ldg(c + 1);
                 b += w[k] * __ldg(c + 2);
@@ -319,8 +319,33 @@ __device__ __forceinline__ void pixel_range(float c, float r, int lo_clip, int h
     hi = min(hi, hi_clip);
 }
 
+// explicit shared-space accesses with 32-bit addresses: inside the hot pixel loop the compiler otherwise rebuilds the
+// generic->shared window base (S2R CgaCtaId + LEA ...) for every access, a third of the loop's instructions
+// (the mov through an opaque asm keeps the value in a register instead of being rematerialised in the loop)
+__device__ __forceinline__ uint32_t sh_addr(const void *p) {
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(p), r;
+    asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(a));
+    return r;
+}
+__device__ __forceinline__ unsigned long long lds_u64_volatile(uint32_t addr) {
+    unsigned long long v;
+    asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_u64(uint32_t addr, unsigned long long v) {
+    asm volatile("st.shared.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
+}
+__device__ __forceinline__ void sts_u16(uint32_t addr, unsigned short v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+}
+
 constexpr int RASTER_QCAP = 512;
-constexpr int RASTER_PCAP = 2048;
+constexpr int RASTER_WPEND = 256;   // accepted fragments a warp buffers before it inserts them
 
 // lock-free sorted insert of one key into a pixel's K slots (chain of atomicMin, see above)
 template <int KMAX>
@@ -334,24 +359,38 @@ __device__ __forceinline__ void klist_insert(unsigned long long *slot, unsigned 
     }
 }
 
-template <int KMAX, bool PER_POINT_CUTOFF, bool BLEND>
-__global__ void __launch_bounds__(RASTER_THREADS, 5)
+// A warp inserts the fragments it has buffered: 32 at a time, all lanes busy.  Other warps may be testing
+// pixels concurrently; they read the K-th key, which only ever decreases, so a stale value merely lets a
+// superfluous fragment into a buffer -- the insert itself re-checks.
+template <int KMAX>
+__device__ __forceinline__ void pend_flush(unsigned long long *s_keys, const unsigned long long *wkey,
+                                           const unsigned short *wpix, int count, int lane) {
+    __syncwarp();
+    for (int i = lane; i < count; i += 32) klist_insert<KMAX>(s_keys + (int)wpix[i] * KMAX, wkey[i]);
+    __syncwarp();
+}
+
+template <int KMAX, bool PER_POINT_CUTOFF, bool BLEND, bool STATS, int MINB>
+__global__ void __launch_bounds__(RASTER_THREADS, MINB)
 raster_sliced_kernel(const __grid_constant__ RasterArgs a) {
     __shared__ unsigned long long s_keys[RASTER_THREADS * KMAX];   // [pixel][k]
     __shared__ int s_queue[RASTER_QCAP];
-    __shared__ unsigned long long s_pend_key[RASTER_PCAP];   // accepted fragments waiting for insertion
-    __shared__ unsigned short s_pend_pix[RASTER_PCAP];
+    __shared__ unsigned long long s_pend_key[RASTER_THREADS / 32][RASTER_WPEND];   // per warp: accepted fragments
+    __shared__ unsigned short s_pend_pix[RASTER_THREADS / 32][RASTER_WPEND];       //           waiting for insertion
+    __shared__ float s_xf[RASTER_TILE], s_yf[RASTER_TILE];   // exact pixel centres of the tile
     __shared__ unsigned int s_blk[16];
-    __shared__ int s_qcount, s_npend;
+    __shared__ int s_qcount;
     __shared__ unsigned int s_tilemax;
 
-    const int S = a.S, B = a.B, K = a.K, NS = a.NS;
+    const int S = a.S, B = a.B, NS = a.NS;
     const int n = blockIdx.y;
     const int tile = blockIdx.x;
     const int ty = tile / B, tx = tile - ty * B;
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t tb = ((int64_t)n * B * B + tile) * NS;
-    const int beg = a.tile_offsets[tb], end = a.tile_offsets[tb + NS];
+    // the id list may have been sized from the previous call (bin_and_raster): never read past it -- if it was too
+    // small the host notices and runs the pass again
+    const int beg = min(a.tile_offsets[tb], a.ids_capacity), end = min(a.tile_offsets[tb + NS], a.ids_capacity);
     const int tx0 = tx * RASTER_TILE, ty0 = ty * RASTER_TILE;
     const int tx1 = min(tx0 + RASTER_TILE, S) - 1, ty1 = min(ty0 + RASTER_TILE, S) - 1;
     const bool pow2 = (S & (S - 1)) == 0;
@@ -363,30 +402,41 @@ raster_sliced_kernel(const __grid_constant__ RasterArgs a) {
 #pragma unroll
         for (int k = 0; k < KMAX; ++k) s_keys[k * RASTER_THREADS + tid] = KEY_EMPTY;
         if (tid < 16) s_blk[tid] = 0xffffffffu;
+        if (tid < RASTER_TILE) {
+            s_xf[tid] = pix_to_ndc(tx0 + tid, S);
+            s_yf[tid] = pix_to_ndc(ty0 + tid, S);
+        }
         if (tid == 0) {
             s_qcount = 0;
-            s_npend = 0;
             s_tilemax = 0xffffffffu;
         }
         __syncthreads();
         const SliceMap sm = make_slice_map(a.zrange, n, NS);
-        for (int s = 0; s < NS; ++s) {
-            const int sb = a.tile_offsets[tb + s], se = a.tile_offsets[tb + s + 1];
-            if (sb == se) continue;
-            // every entry of this and later slices has z >= slice_bound(s): stop if that cannot enter any list
-            if (s > 0 && __float_as_uint(slice_bound(sm, s)) > s_tilemax) {
-                if (tid == 0) st_skip += NS - s;
-                break;
+        unsigned long long *wkey = s_pend_key[warp];
+        unsigned short *wpix = s_pend_pix[warp];
+        const uint32_t sa_kth = sh_addr(s_keys) + (KMAX - 1) * 8, sa_xf = sh_addr(s_xf), sa_yf = sh_addr(s_yf);
+        const uint32_t sa_wkey = sh_addr(wkey), sa_wpix = sh_addr(wpix);
+        // The tile's list is ordered by depth slice: walk it front to back in chunks of 256 entries.  Every entry at
+        // or behind position `base` has z >= slice_bound(slice of base): stop as soon as that cannot enter any list.
+        int base = beg, s_cur = 0;
+        int next_id = (base + tid < end) ? a.tile_ids[base + tid] : 0;     // one chunk ahead
+        while (true) {
+            bool more = base < end;
+            if (more) {
+                while (s_cur + 1 < NS && a.tile_offsets[tb + s_cur + 1] <= base) ++s_cur;   // (offsets beyond the capacity clamp are never reached)
+                if (s_cur > 0 && __float_as_uint(slice_bound(sm, s_cur)) > s_tilemax) {
+                    more = false;
+                    if (STATS && tid == 0) st_skip += NS - s_cur;
+                }
             }
-            if (tid == 0) st_visit++;
-            for (int base = sb; base < se; base += RASTER_THREADS) {
+            if (more) {
                 // ---- phase 1: entry-level cull against the block thresholds, survivors -> queue ----
                 const int j = base + tid;
                 bool survive = false;
-                int id = 0;
-                if (j < se) {
-                    st_scanned++;
-                    id = a.tile_ids[j];
+                const int id = next_id;
+                if (j + RASTER_THREADS < end) next_id = a.tile_ids[j + RASTER_THREADS];
+                if (j < end) {
+                    if (STATS) st_scanned++;
                     const float4 A = __ldg(&a.rec[2 * (int64_t)id]);
                     const float ry = __ldg(&a.rec[2 * (int64_t)id + 1]).x;
                     if (A.z >= 0.0f) {
@@ -408,16 +458,20 @@ raster_sliced_kernel(const __grid_constant__ RasterArgs a) {
                 wbase = __shfl_sync(FULL, wbase, 0);
                 if (survive) {
                     s_queue[wbase + __popc(m & ((1u << lane) - 1u))] = id;
-                    st_surv++;
+                    if (STATS) st_surv++;
                 }
-                __syncthreads();
-                const int nq = s_qcount;
-                __syncthreads();   // everyone has read nq before the next chunk's appends can change it
-                if (nq <= RASTER_QCAP - RASTER_THREADS && base + RASTER_THREADS < se) continue;   // keep filling
-                // ---- phase 2: rasterize the queued survivors, one splat per thread.  Branch-free body inside
-                //      loops whose extents are warp-uniform (max over the warp's 32 splats): lanes whose own
-                //      bbox is smaller are predicated off instead of diverging; accepted fragments are pushed
-                //      with one warp-aggregated atomic per iteration ----
+                base += RASTER_THREADS;
+            }
+            __syncthreads();
+            const int nq = s_qcount;
+            __syncthreads();   // everyone has read nq before the next chunk's appends can change it
+            if (more && nq <= RASTER_QCAP - RASTER_THREADS && base < end) continue;   // keep filling
+            if (nq > 0) {
+                // ---- phase 2: rasterize the queued survivors, one splat per thread: every lane steps through ITS
+                //      splat's pixel rectangle (row-major), the trip count is the largest rectangle of the warp's 32
+                //      splats.  Accepted fragments go to the warp's own buffer (no atomics, no election: the fill
+                //      level is a warp-uniform register) and are inserted 32 at a time when it runs full ----
+                int wcount = 0;
                 for (int ib = 0; ib < nq; ib += RASTER_THREADS) {
                     const int i = ib + tid;
                     const bool have = i < nq;
@@ -427,7 +481,7 @@ raster_sliced_kernel(const __grid_constant__ RasterArgs a) {
                     if (have) {
                         A = __ldg(&a.rec[2 * (int64_t)sid]);
                         Bv = __ldg(&a.rec[2 * (int64_t)sid + 1]);
-                        cut = PER_POINT_CUTOFF ? __ldg(&a.cutoff[sid]) : a.cutoff_uniform;
+                        cut = (PER_POINT_CUTOFF && a.cutoff) ? __ldg(&a.cutoff[sid]) : a.cutoff_uniform;
                     }
                     const unsigned long long key = make_key(A.z + 0.0f, sid);
                     int x0 = tx0, x1 = tx0 - 1, y0 = ty0, y1 = ty0 - 1;
@@ -436,53 +490,48 @@ raster_sliced_kernel(const __grid_constant__ RasterArgs a) {
                         pixel_range(A.y, Bv.x, ty0, ty1, S, inv_S, pow2, half_S, y0, y1);
                     }
                     const int w = max(x1 - x0 + 1, 0), h = max(y1 - y0 + 1, 0);
-                    const int Wm = __reduce_max_sync(FULL, w), Hm = __reduce_max_sync(FULL, h);
-                    for (int iy = 0; iy < Hm; ++iy) {
-                        const int yi = min(y0 + iy, ty1);
-                        const float dy = pix_to_ndc_fast(yi, S, inv_S, pow2) - A.y;
-                        const bool row_ok = (iy < h) && !(fabsf(dy) > Bv.x);
-                        const unsigned long long *row = s_keys + ((yi - ty0) * RASTER_TILE - tx0) * KMAX;
-                        for (int ix = 0; ix < Wm; ++ix) {
-                            const int xi = min(x0 + ix, tx1);
-                            const unsigned long long kth = row[xi * KMAX + KMAX - 1];
-                            const float dx = pix_to_ndc_fast(xi, S, inv_S, pow2) - A.x;
-                            // rasterize_points.cu:94 -- same expression tree for q as the reference
-                            const float qv = Bv.y * dx * dx + Bv.z * dx * dy + Bv.w * dy * dy;
-                            const bool ok = row_ok && (ix < w) && (key < kth) && !(fabsf(dx) > A.w) && !(qv > cut);
-                            st_tests += (row_ok && ix < w) ? 1u : 0u;
-                            const unsigned pm = __ballot_sync(FULL, ok);
-                            if (pm) {
-                                int pbase = 0;
-                                if (lane == __ffs(pm) - 1) pbase = atomicAdd(&s_npend, __popc(pm));
-                                pbase = __shfl_sync(FULL, pbase, __ffs(pm) - 1);
-                                if (ok) {
-                                    st_acc++;
-                                    const int pi = pbase + __popc(pm & ((1u << lane) - 1u));
-                                    const int pixl = (yi - ty0) * RASTER_TILE + (xi - tx0);
-                                    if (pi < RASTER_PCAP) {
-                                        s_pend_key[pi] = key;
-                                        s_pend_pix[pi] = (unsigned short)pixl;
-                                    } else {
-                                        klist_insert<KMAX>(s_keys + pixl * KMAX, key);
-                                    }
-                                }
+                    const int c = w * h;
+                    const int Cm = __reduce_max_sync(FULL, c);
+                    int xl = (c > 0) ? x0 - tx0 : 0, yl = (c > 0) ? y0 - ty0 : 0;
+                    const int xl0 = xl, xl1 = (c > 0) ? x1 - tx0 : 0;
+                    for (int t = 0; t < Cm; ++t) {
+                        const bool active = t < c;
+                        const int pixl = yl * RASTER_TILE + xl;
+                        const unsigned long long kth = lds_u64_volatile(sa_kth + pixl * (KMAX * 8));
+                        const float dx = lds_f32(sa_xf + xl * 4) - A.x;
+                        const float dy = lds_f32(sa_yf + yl * 4) - A.y;
+                        // rasterize_points.cu:92-97 -- same expression tree for q as the reference
+                        const float qv = Bv.y * dx * dx + Bv.z * dx * dy + Bv.w * dy * dy;
+                        const bool ok = active && (key < kth) && !(fabsf(dx) > A.w) && !(fabsf(dy) > Bv.x) && !(qv > cut);
+                        if (STATS) st_tests += active ? 1u : 0u;
+                        const unsigned pm = __ballot_sync(FULL, ok);
+                        if (pm) {
+                            if (wcount + 32 > RASTER_WPEND) {
+                                pend_flush<KMAX>(s_keys, wkey, wpix, wcount, lane);
+                                wcount = 0;
+                            }
+                            if (ok) {
+                                if (STATS) st_acc++;
+                                const int pi = wcount + __popc(pm & ((1u << lane) - 1u));
+                                sts_u64(sa_wkey + pi * 8, key);
+                                sts_u16(sa_wpix + pi * 2, (unsigned short)pixl);
+                            }
+                            wcount += __popc(pm);
+                        }
+                        // next pixel of this lane's rectangle; lanes that are done stay on their last pixel
+                        if (t + 1 < c) {
+                            if (++xl > xl1) {
+                                xl = xl0;
+                                ++yl;
                             }
                         }
                     }
                 }
-                __syncthreads();
-                {
-                    const int np = min(s_npend, RASTER_PCAP);
-                    for (int i = tid; i < np; i += RASTER_THREADS)
-                        klist_insert<KMAX>(s_keys + (int)s_pend_pix[i] * KMAX, s_pend_key[i]);
-                }
+                pend_flush<KMAX>(s_keys, wkey, wpix, wcount, lane);
                 __syncthreads();
                 // ---- phase 3: refresh the block / tile thresholds (K-th depth, pixels outside the image never block) ----
                 if (tid < 16) s_blk[tid] = 0;
-                if (tid == 0) {
-                    s_qcount = 0;
-                    s_npend = 0;
-                }
+                if (tid == 0) s_qcount = 0;
                 __syncthreads();
                 {
                     const int pxl = tid & (RASTER_TILE - 1), pyl = tid >> 4;
@@ -498,10 +547,12 @@ raster_sliced_kernel(const __grid_constant__ RasterArgs a) {
                     s_tilemax = mx;
                 }
                 __syncthreads();
+                if (STATS && tid == 0) st_visit++;
             }
+            if (!more || base >= end) break;
         }
     }
-    if (a.stats) {
+    if (STATS && a.stats) {
         atomicAdd(&a.stats[0], (unsigned long long)st_scanned);
         atomicAdd(&a.stats[1], (unsigned long long)st_surv);
         atomicAdd(&a.stats[2], (unsigned long long)st_tests);
@@ -514,21 +565,27 @@ raster_sliced_kernel(const __grid_constant__ RasterArgs a) {
     raster_epilogue<KMAX, BLEND>(a, s_keys, beg < end, n, tx0, ty0, pow2, inv_S);
 }
 
+
 template <int KMAX>
 static int launch_scatter(dss_ctx *ctx, const RasterArgs &a, cudaStream_t st) {
     dim3 grid((unsigned)(a.B * a.B), (unsigned)a.N);
     StageScope prof(ctx, ST_RASTER_FWD, st);
     const bool blend = a.image != nullptr;
-    if (blend) {
+    if (a.stats) {   // debug counters on: one generic instantiation is enough
+        if (blend) raster_sliced_kernel<KMAX, true, true, true, 4><<<grid, RASTER_THREADS, 0, st>>>(a);
+        else raster_sliced_kernel<KMAX, true, false, true, 4><<<grid, RASTER_THREADS, 0, st>>>(a);
+    } else if (blend) {
         if (a.cutoff)
-            raster_sliced_kernel<KMAX, true, true><<<grid, RASTER_THREADS, 0, st>>>(a);
+            raster_sliced_kernel<KMAX, true, true, false, 4><<<grid, RASTER_THREADS, 0, st>>>(a);
+        else if (ctx->raster_minb5)
+            raster_sliced_kernel<KMAX, false, true, false, 5><<<grid, RASTER_THREADS, 0, st>>>(a);
         else
-            raster_sliced_kernel<KMAX, false, true><<<grid, RASTER_THREADS, 0, st>>>(a);
+            raster_sliced_kernel<KMAX, false, true, false, 4><<<grid, RASTER_THREADS, 0, st>>>(a);
     } else {
         if (a.cutoff)
-            raster_sliced_kernel<KMAX, true, false><<<grid, RASTER_THREADS, 0, st>>>(a);
+            raster_sliced_kernel<KMAX, true, false, false, 4><<<grid, RASTER_THREADS, 0, st>>>(a);
         else
-            raster_sliced_kernel<KMAX, false, false><<<grid, RASTER_THREADS, 0, st>>>(a);
+            raster_sliced_kernel<KMAX, false, false, false, 4><<<grid, RASTER_THREADS, 0, st>>>(a);
     }
     DSS_LAUNCH_CHECK(ctx);
     return DSS_OK;
@@ -571,6 +628,7 @@ int bin_and_raster(dss_ctx *ctx, RasterArgs a, const int64_t *first_idx, const i
     const int S = a.S;
     a.B = (S + RASTER_TILE - 1) / RASTER_TILE;
     a.NS = (a.K <= 8 && !a.force_pixel_parallel) ? choose_depth_slices(a.B) : 1;
+    if (a.NS > 1 && ctx->ns_override > 0 && ctx->ns_override < a.NS) a.NS = ctx->ns_override;
     const int64_t nb = (int64_t)a.N * a.B * a.B * a.NS;
     if (nb + 1 >= (int64_t)INT32_MAX) {
         set_error("too many tiles (%lld)", (long long)nb);
@@ -589,28 +647,46 @@ int bin_and_raster(dss_ctx *ctx, RasterArgs a, const int64_t *first_idx, const i
     if ((rc = bin_count_and_scan(ctx, a.rec, first_idx, num_points, a.N, P0, S, RASTER_TILE, a.NS, zrange, counts,
                                  offsets, st)))
         return rc;
-    // the one host round-trip of the forward pass: size of the CSR id list
-    DSS_CUDA_TRY(cudaMemcpyAsync(ctx->h_pinned, offsets + nb, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    DSS_CUDA_TRY(cudaStreamSynchronize(st));
-    const int64_t total = (int64_t)(*reinterpret_cast<int32_t *>(ctx->h_pinned));
-    if (total < 0) {
-        set_error("tile list size overflowed int32");
-        return DSS_E_INVALID;
-    }
-    if ((rc = ctx_get(ctx, BUF_TILE_IDS, (size_t)(total > 0 ? total : 1), &ids))) return rc;
-    if (total > 0)
-        if ((rc = bin_scatter(ctx, a.rec, first_idx, num_points, a.N, P0, S, RASTER_TILE, a.NS, zrange, offsets, counts,
-                              ids, st)))
-            return rc;
     a.tile_offsets = offsets;
-    a.tile_ids = ids;
     a.stats = nullptr;
     if (ctx->raster_stats) {
         unsigned long long *sp = nullptr;
         if ((rc = ctx_get(ctx, BUF_STATS, 8, &sp))) return rc;
         a.stats = sp;
     }
-    return raster_forward(ctx, a, st);
+    // Size of the CSR id list.  It is only known on the device (last entry of the scan).  Steady state: the list
+    // buffer kept from the previous call is used as is, scatter and rasterizer are enqueued behind the scan without
+    // waiting (both clamp to the buffer's capacity), and only then does the host wait for the scan's total -- the GPU
+    // keeps working on the queued kernels meanwhile.  If the total turns out to exceed the capacity (the cloud or
+    // the cameras changed a lot), the buffer is grown and the two kernels run again.  First call: wait, then size.
+    DSS_CUDA_TRY(cudaMemcpyAsync(ctx->h_pinned, offsets + nb, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    DSS_CUDA_TRY(cudaEventRecord(ctx->ev_total, st));
+    int64_t cap = (int64_t)(ctx->cap[BUF_TILE_IDS] / sizeof(int32_t));
+    bool ran = false;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        if (cap > 0 && !(attempt == 0 && ctx->sync_forward)) {
+            if (cap > (int64_t)INT32_MAX) cap = INT32_MAX;
+            if ((rc = ctx_get(ctx, BUF_TILE_IDS, (size_t)cap, &ids))) return rc;
+            if (attempt > 0 && a.visible && a.visible_count > 0)
+                DSS_CUDA_TRY(cudaMemsetAsync(a.visible, 0, (size_t)a.visible_count, st));   // undo the partial pass
+            if ((rc = bin_scatter(ctx, a.rec, first_idx, num_points, a.N, P0, S, RASTER_TILE, a.NS, zrange, offsets, counts,
+                                  ids, cap, st)))
+                return rc;
+            a.tile_ids = ids;
+            a.ids_capacity = (int)cap;
+            if ((rc = raster_forward(ctx, a, st))) return rc;
+            ran = true;
+        }
+        DSS_CUDA_TRY(cudaEventSynchronize(ctx->ev_total));
+        const int64_t total = (int64_t)(*reinterpret_cast<volatile int32_t *>(ctx->h_pinned));
+        if (total < 0) {
+            set_error("tile list size overflowed int32");
+            return DSS_E_INVALID;
+        }
+        if (ran && total <= cap) break;
+        cap = total + total / 4 + 1024;   // headroom so that slowly growing lists do not trigger a second pass
+    }
+    return DSS_OK;
 }
 
 }  // namespace dss

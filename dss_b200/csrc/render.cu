@@ -342,9 +342,11 @@ int dss_render_forward(dss_ctx *ctx, const dss_render_args *g, void *stream) {
     a.occ = nullptr;
     a.scaler = g->scaler;
     a.colours = g->colours;
+    a.colour_P0 = (g->shared_cloud && g->shared_colours) ? g->P0 : 0;
     a.image = g->image;
     a.weights = g->weights;
     a.visible = g->visible;
+    a.visible_count = g->P;
     a.zrange = zrange;   // already filled by the preprocess kernel
     return bin_and_raster(ctx, a, g->shared_cloud ? nullptr : g->first_idx, g->num_points, g->P0, st);
 }
@@ -371,15 +373,25 @@ int dss_render_backward(dss_ctx *ctx, const dss_render_args *g, void *stream) {
     }
     if ((rc = ctx_get(ctx, BUF_RS, (size_t)N, &rs))) return rc;
     if ((rc = ctx_get(ctx, BUF_GRADXY, (size_t)(2 * P), &gxy))) return rc;
+    // The colour scatter does not depend on the occupancy path: fork it onto the context's side stream so that its
+    // atomics overlap the (latency-bound) binning / median kernels, join before returning to the caller's stream.
+    const bool fork_colours = g->grad_colours != nullptr;
+    if (fork_colours) {
+        DSS_CUDA_TRY(cudaEventRecord(ctx->ev_fork, st));
+        DSS_CUDA_TRY(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+        const int64_t cP0 = (g->shared_cloud && g->shared_colours) ? g->P0 : 0;
+        DSS_CUDA_TRY(cudaMemsetAsync(g->grad_colours, 0, (size_t)(cP0 > 0 ? cP0 : P) * 3 * sizeof(float), ctx->side));
+        if ((rc = colour_backward(ctx, g->idx, g->weights, g->grad_image, npix, K, g->grad_colours, cP0, (int64_t)S * S,
+                                  ctx->side)))
+            return rc;
+        DSS_CUDA_TRY(cudaEventRecord(ctx->ev_join, ctx->side));
+    }
     if ((rc = occ_backward(ctx, rec, g->visible, rs, g->radii_backward_scaler, g->grad_image, 4, 3, fi, g->num_points, N,
                            g->P0, S, gxy, st)))
         return rc;
     if (g->search_radius)
         DSS_CUDA_TRY(cudaMemcpyAsync(g->search_radius, rs, (size_t)N * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    if (g->grad_colours) {
-        DSS_CUDA_TRY(cudaMemsetAsync(g->grad_colours, 0, (size_t)P * 3 * sizeof(float), st));
-        if ((rc = colour_backward(ctx, g->idx, g->weights, g->grad_image, npix, K, g->grad_colours, st))) return rc;
-    }
+    if (fork_colours) DSS_CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_join, 0));
     float *gz = nullptr;
     if (g->grad_zbuf) {
         if ((rc = ctx_get(ctx, BUF_MISC, (size_t)P, &gz))) return rc;

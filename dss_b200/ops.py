@@ -91,8 +91,10 @@ class _RenderFunction(torch.autograd.Function):
         view_c = _lib.as_f32(view.detach(), "view")
         h_c = _lib.as_f32(h.detach().reshape(-1), "h")
         N, P0, P = _layout(points_c, proj_c, first_idx, num_points, shared)
-        if tuple(colours_c.shape) != (P, 3):
-            raise RuntimeError("colours must have shape (%d, 3), got %s" % (P, tuple(colours_c.shape)))
+        shared_col = bool(shared) and N > 1 and tuple(colours_c.shape) == (P0, 3)
+        if tuple(colours_c.shape) != (P, 3) and not shared_col:
+            raise RuntimeError("colours must have shape (%d, 3)%s, got %s"
+                               % (P, " or (%d, 3)" % P0 if shared else "", tuple(colours_c.shape)))
         if tuple(proj_c.shape) != (N, 4, 4) or tuple(view_c.shape) != (N, 4, 4):
             raise RuntimeError("proj and view must have shape (N,4,4)")
         if h_c.numel() not in (N, P):
@@ -113,13 +115,17 @@ class _RenderFunction(torch.autograd.Function):
         npts = num_points.contiguous() if num_points is not None else None
         a = _lib.RenderArgs()
         _fill_common(a, points_c, normals_c, colours_c, proj_c, view_c, h_c, fi, npts, shared, N, P0, P, prm)
+        a.shared_colours = int(shared_col)
         a.records, a.scaler, a.image, a.idx = _lib.ptr(records), _lib.ptr(scaler), _lib.ptr(image), _lib.ptr(idx)
         a.weights, a.visible, a.zbuf, a.qvalue = _lib.ptr(weights), _lib.ptr(visible), _lib.ptr(zbuf), _lib.ptr(qvalue)
         with torch.cuda.device(dev):
             rc = _lib.load().dss_render_forward(_lib.ctx(dev), C.byref(a), _lib.stream_ptr(dev))
         _lib.check(rc, "dss_render_forward")
+        # no zero-filled gradients for the outputs nobody differentiates (idx, weights, records ... would cost five
+        # fill kernels over ~400 MB per backward); backward() handles None
+        ctx.set_materialize_grads(False)
         ctx.save_for_backward(points_c, proj_c, view_c, records, idx, weights, visible, fi, npts)
-        ctx.meta = (shared, prm, N, P0, P, want_frags)
+        ctx.meta = (shared, prm, N, P0, P, want_frags, shared_col)
         outs = (image, idx, weights, visible, records, scaler)
         if want_frags:
             ctx.mark_non_differentiable(idx, weights, visible, records, scaler, qvalue)
@@ -130,7 +136,7 @@ class _RenderFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_image, *rest):
         points_c, proj_c, view_c, records, idx, weights, visible, fi, npts = ctx.saved_tensors
-        shared, prm, N, P0, P, want_frags = ctx.meta
+        shared, prm, N, P0, P, want_frags, shared_col = ctx.meta
         dev = points_c.device
         grad_zbuf = rest[5] if (want_frags and len(rest) > 5) else None
         if grad_image is None:
@@ -138,11 +144,12 @@ class _RenderFunction(torch.autograd.Function):
         grad_image = _lib.as_f32(grad_image, "grad_image")
         if grad_zbuf is not None:
             grad_zbuf = _lib.as_f32(grad_zbuf, "grad_zbuf")
-        grad_colours = torch.empty((P, 3), dtype=torch.float32, device=dev)
+        grad_colours = torch.empty((P0 if shared_col else P, 3), dtype=torch.float32, device=dev)
         grad_points = torch.empty_like(points_c)
         a = _lib.RenderArgs()
         _fill_common(a, points_c, None, None, proj_c, view_c, None, fi, npts, shared, N, P0, P, prm)
         a.records, a.idx, a.weights, a.visible = _lib.ptr(records), _lib.ptr(idx), _lib.ptr(weights), _lib.ptr(visible)
+        a.shared_colours = int(shared_col)
         a.grad_image, a.grad_zbuf = _lib.ptr(grad_image), _lib.ptr(grad_zbuf)
         a.grad_colours, a.grad_points_world = _lib.ptr(grad_colours), _lib.ptr(grad_points)
         with torch.cuda.device(dev):
@@ -156,7 +163,8 @@ def render_points(points, normals, colours, proj, view, h, params: SplatParams, 
     """Render ``N`` views of an oriented point cloud to RGBA.
 
     points, normals : (P0,3) when ``shared_cloud`` (one cloud seen from N cameras) else packed (P,3)
-    colours         : (N*P0,3) / (P,3) per-(view,point) features (e.g. shaded rgb)
+    colours         : (N*P0,3) / (P,3) per-(view,point) features (e.g. shaded rgb), or (P0,3) per-point
+                      features used by every view of a shared cloud (gradient then summed over the views)
     proj, view      : (N,4,4) full-projection and world-to-view matrices, row-vector convention
     h               : (N,) per-view or (P,) per-splat variance scale (rasterizer.py:293-402)
     """

@@ -166,7 +166,7 @@ typedef struct dss_render_args {
      * otherwise packed (P,3) with first_idx/num_points as above. */
     const float *points_world;     /* (P0,3) or (P,3)                                            */
     const float *normals_world;    /* same shape, unit length                                    */
-    const float *colours;          /* (P,3) per (view,point) features, e.g. shaded rgb            */
+    const float *colours;          /* (P,3) per (view,point) features, e.g. shaded rgb; (P0,3) if shared_colours */
     const float *proj;             /* (N,4,4) full projection, row-vector convention [x y z 1] M  */
     const float *view;             /* (N,4,4) world-to-view, same convention                      */
     const float *h;                /* (N,) variance scale per view, or (P,) per splat             */
@@ -203,10 +203,15 @@ typedef struct dss_render_args {
     /* backward */
     const float *grad_image;       /* (N,S,S,4)                                                    */
     const float *grad_zbuf;        /* (N,S,S,K) or NULL                                            */
-    float *grad_colours;           /* (P,3)                                                        */
+    float *grad_colours;           /* (P,3), or (P0,3) if shared_colours                           */
     float *grad_ndc;               /* (P,3) gradient w.r.t. ndc (after clipping)                   */
     float *grad_points_world;      /* (P0,3) summed over views when shared_cloud, else (P,3)       */
     float *search_radius;          /* (N,) out                                                     */
+    /* != 0 (shared_cloud only): `colours` is (P0,3), one feature row per POINT used by every view (view-independent
+     * colour, the common host-side input: the reference only materialises the (N*P0,3) tensor on the device, after
+     * shading) and `grad_colours` is (P0,3), summed over the views. */
+    int32_t shared_colours;
+    int32_t reserved0;
 } dss_render_args;
 
 /* preprocess -> bin -> rasterize + blend.  Synchronises the stream once (tile-list size). */

@@ -149,3 +149,26 @@ def test_backward_is_deterministic_and_linear_in_grad(cuda_device):
     a, b, c2 = run(1.0), run(1.0), run(2.0)
     assert torch.equal(a, b)
     torch.testing.assert_close(c2, 2 * a, rtol=1e-5, atol=1e-9)
+
+
+def test_shared_point_colours_equal_repeated_colours(cuda_device):
+    """colours given once per POINT (P0,3) render exactly like the same rows repeated for every view, and their
+    gradient is the sum over the views of the per-(view,point) gradient."""
+    P0, N, S = 12000, 3, 96
+    pts, nrm, col, proj, view, cams = scene(P0, N, seed=11)
+    d = cuda_device
+    prm = SplatParams(image_size=S, znear=0.1, clip_pts_grad=0.05)
+    h = torch.full((N,), 3e-4).to(d)
+    g = (torch.randn(N, S, S, 4, generator=torch.Generator().manual_seed(4)) * 1e-3).to(d)
+    p1 = pts.to(d).requires_grad_(True)
+    c1 = col.repeat(N, 1).to(d).requires_grad_(True)
+    o1 = render_points(p1, nrm.to(d), c1, proj.to(d), view.to(d), h, prm)
+    o1.image.backward(g)
+    p2 = pts.to(d).requires_grad_(True)
+    c2 = col.to(d).requires_grad_(True)
+    o2 = render_points(p2, nrm.to(d), c2, proj.to(d), view.to(d), h, prm)
+    o2.image.backward(g)
+    assert torch.equal(o1.image, o2.image) and torch.equal(o1.idx, o2.idx)
+    assert torch.equal(p1.grad, p2.grad)
+    assert tuple(c2.grad.shape) == (P0, 3)
+    torch.testing.assert_close(c2.grad, c1.grad.view(N, P0, 3).sum(0), rtol=1e-4, atol=1e-9)
