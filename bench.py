@@ -357,8 +357,16 @@ def run_ours(a):
         ev_done = [torch.cuda.Event() for _ in range(2)]
         ev_out = [torch.cuda.Event() for _ in range(2)]
         state = {"i": 0}
+        keep = [None, None]     # outputs of the step that last used a slot: alive until their read-back has finished
 
         diag = os.environ.get("BENCH_E2E_SKIP", "")   # diagnosis only: "h2d" / "d2h" drop that half of the traffic
+        trace = [] if os.environ.get("BENCH_E2E_TRACE") else None   # diagnosis only: device timeline of the e2e loop
+
+        def mark(name, stream):
+            if trace is not None and state["i"] >= 3:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(stream)
+                trace.append((state["i"], name, e))
 
         def stage_inputs(slot):
             if "h2d" in diag and state["i"] > 2:
@@ -366,9 +374,11 @@ def run_ours(a):
                 return
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(ev_done[slot])      # the previous user of this slot has finished
+                mark("h2d_begin(for step+1)", copy_stream)
                 for d, hsrc in zip(dev_in[slot], host_in):
                     d.copy_(hsrc, non_blocking=True)
                 ev_in[slot].record(copy_stream)
+                mark("h2d_end(for step+1)", copy_stream)
 
         def step_e2e():
             i = state["i"]
@@ -380,24 +390,30 @@ def run_ours(a):
             main.wait_event(ev_in[slot])
             main.wait_event(ev_out[slot])                  # result buffers of two steps ago have been read back
             d = dev_in[slot]
+            mark("compute_begin", main)
             p = d[0].detach().requires_grad_(True)
             c = d[2].detach().requires_grad_(True)
             out = render_points(p, d[1], c, d[3], d[4], d[5], prm)
+            mark("forward_end", main)
             out.image.backward(d[6])
             ev_done[slot].record(main)
+            mark("compute_end", main)
             with torch.cuda.stream(back_stream):
                 back_stream.wait_event(ev_done[slot])
                 if "d2h" in diag:
                     ev_out[slot].record(back_stream)
                     state["i"] = i + 1
                     return
+                mark("d2h_begin", back_stream)
                 img_h.copy_(out.image.detach(), non_blocking=True)
                 gpts_h.copy_(p.grad, non_blocking=True)
                 gcol_h.copy_(c.grad, non_blocking=True)
                 ev_out[slot].record(back_stream)
-            out.image.record_stream(back_stream)
-            p.grad.record_stream(back_stream)
-            c.grad.record_stream(back_stream)
+                mark("d2h_end", back_stream)
+            # no record_stream(): the tensors the read-back reads stay referenced until this slot comes round again, and by
+            # then the main stream has waited for ev_out[slot] -- the caching allocator sees a plain same-stream free
+            # (record_stream defers reuse unpredictably and costs occasional cudaMalloc/cudaFree stalls of ~15 ms)
+            keep[slot] = (out, p, c)
             state["i"] = i + 1
 
         h2d = sum(x.numel() * x.element_size() for x in host_in)
@@ -413,6 +429,10 @@ def run_ours(a):
         torch.cuda.current_stream(dev).wait_stream(back_stream)   # the last read-back is inside the timed region
         f1.record()
         sync_all()
+        if trace:
+            base = trace[0][2]
+            for i, name, e in trace[:60]:
+                print("trace step %d %-22s %8.3f ms" % (i, name, base.elapsed_time(e)), file=sys.stderr)
         t2 = torch.tensor([f0.elapsed_time(f1)], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t2, op=dist.ReduceOp.MAX)

@@ -441,7 +441,7 @@ int dss_rasterize_coarse(dss_ctx *ctx, const float *points, const float *radii, 
     if ((rc = pack_records(ctx, points, radii, nullptr, P, rec, st))) return rc;
     if ((rc = bin_count_and_scan(ctx, rec, first_idx, num_points, N, P, S, bin_size, 1, nullptr, counts, bin_offsets, st)))
         return rc;
-    DSS_CUDA_TRY(cudaMemcpyAsync(ctx->h_pinned, bin_offsets + nb, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if ((rc = publish_words(ctx, bin_offsets + nb, ctx->h_pinned, 1, st))) return rc;
     DSS_CUDA_TRY(cudaStreamSynchronize(st));
     const int64_t total = (int64_t)(*reinterpret_cast<int32_t *>(ctx->h_pinned));
     if (total_required_host) *total_required_host = total;

@@ -98,7 +98,6 @@ struct dss_ctx {
     cudaEvent_t ev_fork, ev_join;
     const void *occ_counts_ptr;   // BUF_OCC_COUNTS block known to be all zero (nullptr: unknown)
     size_t occ_counts_elems;
-    int occ_lps8;           // tuning (env DSS_OCC_LPS8=1): 8 lanes x 2 column pairs per splat instead of 4 x 4
     int ns_override;    // tuning (env DSS_NS): number of depth slices of the forward tile lists, 0 = automatic
     int bin_direct;     // tuning (env DSS_BIN_DIRECT): tile binning with plain global atomics instead of per-block histograms
     double stage_ms[dss::NUM_STAGES];

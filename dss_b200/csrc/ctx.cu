@@ -226,6 +226,21 @@ scan_kernel(const int32_t *in, int32_t *out, int64_t n, unsigned long long *stat
     }
 }
 
+__global__ void publish_words_kernel(const uint32_t *__restrict__ src, uint32_t *dst, int n) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+    __threadfence_system();
+}
+
+int publish_words(dss_ctx *ctx, const void *src_device, void *dst_pinned_host, int n_words, cudaStream_t st) {
+    if (n_words <= 0) return DSS_OK;
+    void *dst_dev = nullptr;
+    DSS_CUDA_TRY(cudaHostGetDevicePointer(&dst_dev, dst_pinned_host, 0));
+    publish_words_kernel<<<1, 128, 0, st>>>(reinterpret_cast<const uint32_t *>(src_device),
+                                           reinterpret_cast<uint32_t *>(dst_dev), n_words);
+    DSS_LAUNCH_CHECK(ctx);
+    return DSS_OK;
+}
+
 int exclusive_scan_i32(dss_ctx *ctx, const int32_t *in, int32_t *out, int64_t n, cudaStream_t st) {
     if (n <= 0) return DSS_OK;
     const int64_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
@@ -273,17 +288,13 @@ int dss_create(dss_ctx **out) {
         const char *ns = getenv("DSS_NS");
         c->ns_override = ns ? atoi(ns) : 0;
     }
-    if (cudaMallocHost((void **)&c->h_pinned, 64 * sizeof(int64_t)) != cudaSuccess) {
+    if (cudaHostAlloc((void **)&c->h_pinned, 64 * sizeof(int64_t), cudaHostAllocMapped) != cudaSuccess) {
         cudaGetLastError();
         delete c;
         dss::set_error("pinned host allocation failed");
         return DSS_E_NOMEM;
     }
     memset(c->h_pinned, 0, 64 * sizeof(int64_t));
-    {
-        const char *l8 = getenv("DSS_OCC_LPS8");
-        c->occ_lps8 = (l8 && l8[0] == '1') ? 1 : 0;
-    }
     if (cudaEventCreateWithFlags(&c->ev_total, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess ||

@@ -6,6 +6,12 @@ namespace dss {
 
 constexpr int RASTER_TILE = 16;  // pixels per side of a raster tile (one 256-thread CTA)
 
+// Small device -> host read-back WITHOUT the copy engine: a one-block kernel stores the words straight into pinned,
+// device-mapped host memory.  A cudaMemcpyAsync would queue behind whatever large D2H copy another stream has in
+// flight (copies of one direction are served in order) and, being in stream order, stall every kernel enqueued
+// after it -- measured: ~1 ms per step in bench.py's end-to-end loop while the previous step's image is read back.
+int publish_words(dss_ctx *ctx, const void *src_device, void *dst_pinned_host, int n_words, cudaStream_t st);
+
 int exclusive_scan_i32(dss_ctx *ctx, const int32_t *in, int32_t *out, int64_t n, cudaStream_t st);
 
 int pack_records(dss_ctx *ctx, const float *points, const float *radii, const float *ellipse, int64_t P,

@@ -26,8 +26,6 @@
 namespace dss {
 
 constexpr int OCC_TILE = 32;            // pixels per side of a backward tile
-constexpr int OCC_CONSUMERS = 8;        // consumer warps of the tile kernel (+ 1 producer warp)
-constexpr int OCC_THREADS = (OCC_CONSUMERS + 1) * 32;
 constexpr int OCC_ITEM = 128;           // splats per work item (= records staged per TMA copy)
 constexpr int OCC_GROUP = 4;            // consecutive items handed to one CTA
 constexpr int OCC_SLACK = 64;           // floats of slack behind each staged plane / the column table
@@ -390,7 +388,6 @@ struct OccTileArgs {
     const float *planes;         // (N, 2, Hp, W)
     float2 *grad_xy;             // (P,) out
     int S, OB, R_box, side, W, Hp;
-    int lps8;                    // tuning: 8 lanes x 2 pairs instead of 4 lanes x 3..4 pairs for 17..32 columns
     int64_t nt;
 };
 
@@ -457,7 +454,7 @@ __device__ __forceinline__ void occ_rows(int j0, int j1, const float *__restrict
 }
 
 // One staged item: `cnt` splats of one tile.  Warp w takes batches w, w + 8, ...; a batch is 32 / LPS splats.
-template <int LPS, int PPL, bool POW2>
+template <int LPS, int PPL, bool POW2, int NCONS>
 __device__ __forceinline__ void occ_item(const OccTileArgs &a, const OccItem &it, const float *__restrict__ s_gm,
                                          const float *__restrict__ s_gp, const float *__restrict__ s_xf,
                                          const float *__restrict__ s_yf, const float4 *__restrict__ s_rec, int warp,
@@ -472,7 +469,7 @@ __device__ __forceinline__ void occ_item(const OccTileArgs &a, const OccItem &it
     const float pixf = 2.0f / (float)S;
     const float2 pix2 = make_float2(pixf, pixf);
     const float r2 = it.r2;
-    for (int b = warp; b * GROUPS < it.cnt; b += OCC_CONSUMERS) {
+    for (int b = warp; b * GROUPS < it.cnt; b += NCONS) {
         const int k = b * GROUPS + grp;
         const bool have = k < it.cnt;
         const float4 rc = s_rec[have ? k : 0];
@@ -531,9 +528,10 @@ __device__ __forceinline__ void occ_item(const OccTileArgs &a, const OccItem &it
 // window buffer when the tile changes, the item's records into the free record buffer), completion signalled on the
 // slot's "full" mbarrier; warps 0-7 are CONSUMERS -- they wait on "full", gather, and release the slot through its
 // "empty" mbarrier.  Two item slots and two window buffers are in flight, so staging overlaps the arithmetic.
-template <bool POW2>
-__global__ void __launch_bounds__(OCC_THREADS, 2)
+template <bool POW2, int NCONS>
+__global__ void __launch_bounds__((NCONS + 1) * 32, 2)
 occ_tile_kernel(const __grid_constant__ OccTileArgs a) {
+    constexpr int OCC_THREADS = (NCONS + 1) * 32;
     extern __shared__ __align__(128) unsigned char occ_smem[];
     const int S = a.S, OB = a.OB, side = a.side, R_box = a.R_box;
     const int plane_elems = side * side + OCC_SLACK;
@@ -548,8 +546,8 @@ occ_tile_kernel(const __grid_constant__ OccTileArgs a) {
     if (tid == 0) {
         mbar_init(bar_full, 1);
         mbar_init(bar_full + 8, 1);
-        mbar_init(bar_empty, OCC_CONSUMERS);
-        mbar_init(bar_empty + 8, OCC_CONSUMERS);
+        mbar_init(bar_empty, NCONS);
+        mbar_init(bar_empty + 8, NCONS);
         mbar_fence_init();
     }
     // the slack behind the planes / column table is read (and masked out) by lanes whose column pairs lie beyond
@@ -567,7 +565,7 @@ occ_tile_kernel(const __grid_constant__ OccTileArgs a) {
     // sequence number q of this CTA's items: group = blockIdx.x + (q / OCC_GROUP) * gridDim.x, item = group*G + q%G
     const int q_end = my_groups * OCC_GROUP;
 
-    if (warp == OCC_CONSUMERS) {
+    if (warp == NCONS) {
         // ------------------------------- producer -------------------------------
         int wt_cur = -1;                       // tile held by the current window buffer
         int wcur = 0;
@@ -654,14 +652,13 @@ occ_tile_kernel(const __grid_constant__ OccTileArgs a) {
         const float *s_gm = w, *s_gp = w + plane_elems, *s_xf = w + 2 * plane_elems, *s_yf = s_xf + side + OCC_SLACK;
         const float4 *rec = s_rec + slot * OCC_ITEM;
         const int need = 2 * it.hh + 2;          // window columns + 1 for the shift to an even column
-        if (need <= 8) occ_item<4, 1, POW2>(a, it, s_gm, s_gp, s_xf, s_yf, rec, warp, lane);
-        else if (need <= 16) occ_item<4, 2, POW2>(a, it, s_gm, s_gp, s_xf, s_yf, rec, warp, lane);
-        else if (need <= 32 && a.lps8) occ_item<8, 2, POW2>(a, it, s_gm, s_gp, s_xf, s_yf, rec, warp, lane);
-        else if (need <= 24) occ_item<4, 3, POW2>(a, it, s_gm, s_gp, s_xf, s_yf, rec, warp, lane);
-        else if (need <= 32) occ_item<4, 4, POW2>(a, it, s_gm, s_gp, s_xf, s_yf, rec, warp, lane);
-        else if (need <= 48) occ_item<8, 3, POW2>(a, it, s_gm, s_gp, s_xf, s_yf, rec, warp, lane);
-        else if (need <= 64) occ_item<8, 4, POW2>(a, it, s_gm, s_gp, s_xf, s_yf, rec, warp, lane);
-        else occ_item<16, 3, POW2>(a, it, s_gm, s_gp, s_xf, s_yf, rec, warp, lane);   // need <= 96 (R_box <= 40)
+        if (need <= 8) occ_item<4, 1, POW2, NCONS>(a, it, s_gm, s_gp, s_xf, s_yf, rec, warp, lane);
+        else if (need <= 16) occ_item<4, 2, POW2, NCONS>(a, it, s_gm, s_gp, s_xf, s_yf, rec, warp, lane);
+        else if (need <= 24) occ_item<4, 3, POW2, NCONS>(a, it, s_gm, s_gp, s_xf, s_yf, rec, warp, lane);
+        else if (need <= 32) occ_item<4, 4, POW2, NCONS>(a, it, s_gm, s_gp, s_xf, s_yf, rec, warp, lane);
+        else if (need <= 48) occ_item<8, 3, POW2, NCONS>(a, it, s_gm, s_gp, s_xf, s_yf, rec, warp, lane);
+        else if (need <= 64) occ_item<8, 4, POW2, NCONS>(a, it, s_gm, s_gp, s_xf, s_yf, rec, warp, lane);
+        else occ_item<16, 3, POW2, NCONS>(a, it, s_gm, s_gp, s_xf, s_yf, rec, warp, lane);   // need <= 96 (R_box <= 40)
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_empty + 8 * slot);
     }
@@ -875,7 +872,6 @@ int occ_backward(dss_ctx *ctx, const float4 *rec, const uint8_t *visible, float 
         a.W = W;
         a.Hp = Hp;
         a.nt = nt;
-        a.lps8 = ctx->occ_lps8;
         const bool pow2 = (S & (S - 1)) == 0;
         // persistent: as many CTAs as fit (2 per SM at the usual window sizes), items round-robin in groups
         int per_sm = (int)((size_t)220 * 1024 / (smem + 1024));
@@ -884,13 +880,14 @@ int occ_backward(dss_ctx *ctx, const float4 *rec, const uint8_t *visible, float 
         int64_t want = (max_items + OCC_GROUP - 1) / OCC_GROUP;
         unsigned tgrid = (unsigned)(want < (int64_t)ctx->sm_count * per_sm ? want : (int64_t)ctx->sm_count * per_sm);
         if (tgrid < 1) tgrid = 1;
-        if (pow2) {
-            DSS_CUDA_TRY(cudaFuncSetAttribute(occ_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            occ_tile_kernel<true><<<tgrid, OCC_THREADS, smem, st>>>(a);
-        } else {
-            DSS_CUDA_TRY(cudaFuncSetAttribute(occ_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            occ_tile_kernel<false><<<tgrid, OCC_THREADS, smem, st>>>(a);
-        }
+        auto launch = [&](auto kern, int threads) -> int {
+            DSS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<tgrid, threads, smem, st>>>(a);
+            return DSS_OK;
+        };
+        // 8 consumer warps + 1 producer warp per CTA (10 consumers measured 20 % slower: 80 registers spill)
+        rc = pow2 ? launch(occ_tile_kernel<true, 8>, 9 * 32) : launch(occ_tile_kernel<false, 8>, 9 * 32);
+        if (rc) return rc;
         DSS_LAUNCH_CHECK(ctx);
     } else if (compute_rs) {
         if ((rc = search_radius(ctx, rec, nullptr, visible, first_idx, num_points, N, P0, radii_s, rs, st))) return rc;
@@ -905,8 +902,7 @@ int occ_backward(dss_ctx *ctx, const float4 *rec, const uint8_t *visible, float 
         DSS_LAUNCH_CHECK(ctx);
     }
     // refresh the hint for the next call (asynchronous; may be read stale, it is only a hint)
-    DSS_CUDA_TRY(cudaMemcpyAsync(h_rs, rs, (size_t)(N < 96 ? N : 96) * sizeof(float), cudaMemcpyDeviceToHost, st));
-    return DSS_OK;
+    return publish_words(ctx, rs, h_rs, N < 96 ? N : 96, st);
 }
 
 }  // namespace dss

@@ -659,7 +659,7 @@ int bin_and_raster(dss_ctx *ctx, RasterArgs a, const int64_t *first_idx, const i
     // waiting (both clamp to the buffer's capacity), and only then does the host wait for the scan's total -- the GPU
     // keeps working on the queued kernels meanwhile.  If the total turns out to exceed the capacity (the cloud or
     // the cameras changed a lot), the buffer is grown and the two kernels run again.  First call: wait, then size.
-    DSS_CUDA_TRY(cudaMemcpyAsync(ctx->h_pinned, offsets + nb, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if ((rc = publish_words(ctx, offsets + nb, ctx->h_pinned, 1, st))) return rc;
     DSS_CUDA_TRY(cudaEventRecord(ctx->ev_total, st));
     int64_t cap = (int64_t)(ctx->cap[BUF_TILE_IDS] / sizeof(int32_t));
     bool ran = false;
