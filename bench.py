@@ -396,6 +396,12 @@ def run_ours(a):
             out = render_points(p, d[1], c, d[3], d[4], d[5], prm)
             mark("forward_end", main)
             out.image.backward(d[6])
+            if world > 1:
+                # the one exchange step of the path: sum of the point gradients over all ranks' views
+                sync = torch.cat([p.grad, c.grad], 1)
+                dist.all_reduce(sync)
+                p.grad.copy_(sync[:, :3])
+                c.grad.copy_(sync[:, 3:])
             ev_done[slot].record(main)
             mark("compute_end", main)
             with torch.cuda.stream(back_stream):
@@ -453,14 +459,17 @@ def run_ours(a):
     alg = {
         # algorithmic bytes per launch (one launch covers the V views of a step); DESIGN.md "Roofline"
         "raster_forward": per_launch_views * (36 * P0 + (16 + 4 * K) * S * S),
-        "occ_backward": per_launch_views * (4 * S * S + 20 * P0 + 8 * P0),
+        # planes (read alpha 16 B/px of the image gradient, write 2 planes) + gather (read both planes once, read the
+        # compact records of the visible splats, write their gradients): upper bound with P_vis = P0
+        "occ_backward": per_launch_views * ((16 + 8) * S * S + 8 * S * S + 28 * P0),
+        "occ_bin": per_launch_views * 9 * P0,
         "preprocess": per_launch_views * (24 * P0 + 36 * P0),
         "bin_count": per_launch_views * 20 * P0, "bin_scatter": per_launch_views * 24 * P0,
         "colour_backward": per_launch_views * ((16 + 8 * K) * S * S + 12 * P0),
         "chain_world": per_launch_views * 20 * P0 + 24 * P0,
         "search_radius": per_launch_views * 4 * 9 * P0,
     }.get(dom, 0)
-    dom_avg_ms = dom_ms / max(dom_n, 1)
+    dom_avg_ms = dom_ms / max(a.steps, 1)      # per step: a stage's kernels are launched once per step
     achieved = alg / (dom_avg_ms * 1e-3) / 1e9 if dom_avg_ms > 0 else 0.0
     step_bytes = V * algorithmic_bytes_per_view(P0, S, K)
     step_gbs = step_bytes / (ms_max / a.steps * 1e-3) / 1e9

@@ -350,6 +350,9 @@ constexpr int RASTER_WPEND = 256;   // accepted fragments a warp buffers before 
 // lock-free sorted insert of one key into a pixel's K slots (chain of atomicMin, see above)
 template <int KMAX>
 __device__ __forceinline__ void klist_insert(unsigned long long *slot, unsigned long long carry) {
+    // most buffered fragments are stale by the time they are inserted (the pixel's K-th key has dropped below them
+    // since the test): one load settles those
+    if (carry >= slot[KMAX - 1]) return;
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
         if (carry < slot[k]) {

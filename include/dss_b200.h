@@ -67,7 +67,8 @@ DSS_API int dss_profile_read(dss_ctx *ctx, int stage, double *total_ms, int64_t 
 
 /* Debug work counters of the depth-sliced rasterizer (off by default; adds global atomics when on):
  * out[0] tile-list entries scanned, [1] survivors of the block-threshold cull, [2] (splat,pixel) tests,
- * [3] accepted fragments queued for insertion, [4] slices skipped by early termination, [5] slices visited.
+ * [3] accepted fragments queued for insertion, [4] slices skipped by early termination, [5] rasterization passes
+ * (queue flushes) executed.
  * enable != 0 switches collection on (and zeroes the counters); out may be NULL. Synchronises the device. */
 DSS_API int dss_debug_raster_stats(dss_ctx *ctx, int enable, uint64_t out[8]);
 
@@ -214,7 +215,8 @@ typedef struct dss_render_args {
     int32_t reserved0;
 } dss_render_args;
 
-/* preprocess -> bin -> rasterize + blend.  Synchronises the stream once (tile-list size). */
+/* preprocess -> bin -> rasterize + blend.  Waits once for the event that marks the tile-list size (the kernels
+ * behind it are already queued from the second call on; see DESIGN.md "Host side"). */
 DSS_API int dss_render_forward(dss_ctx *ctx, const dss_render_args *args, void *stream);
 /* visibility/median radius -> occupancy gather -> colour scatter -> z scatter -> clip -> world chain. */
 DSS_API int dss_render_backward(dss_ctx *ctx, const dss_render_args *args, void *stream);
