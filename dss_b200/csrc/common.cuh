@@ -61,6 +61,9 @@ enum BufId {
     BUF_OCC_ITEMS,    // tile of every work item
     BUF_OCC_COUNTS,   // per-tile counters of the occupancy binning (kept at zero between calls)
     BUF_OCC_IDS,      // packed splat id of every compact record
+    BUF_KNN_COUNTS,   // 3-D grid of the K-NN search: points per cell
+    BUF_KNN_OFFSETS,  //   exclusive scan of the counts
+    BUF_KNN_SORTED,   //   points in cell order {x, y, z, index}
     NUM_BUFS
 };
 
@@ -69,7 +72,7 @@ enum BufId {
 namespace dss {
 enum Stage {
     ST_PACK = 0, ST_PREPROCESS, ST_BIN_COUNT, ST_SCAN, ST_BIN_SCATTER, ST_RASTER_FWD, ST_VISIBILITY,
-    ST_SEARCH_RADIUS, ST_OCC_BWD, ST_COLOUR_BWD, ST_ZBUF_BWD, ST_CHAIN, ST_GRID, ST_OCC_BIN, NUM_STAGES
+    ST_SEARCH_RADIUS, ST_OCC_BWD, ST_COLOUR_BWD, ST_ZBUF_BWD, ST_CHAIN, ST_GRID, ST_OCC_BIN, ST_KNN, NUM_STAGES
 };
 struct ProfPending {
     cudaEvent_t a, b;

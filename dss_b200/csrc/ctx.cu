@@ -101,7 +101,7 @@ static void prof_collect(dss_ctx *ctx) {
 
 static const char *k_stage_names[NUM_STAGES] = {
     "pack_records", "preprocess", "bin_count", "scan", "bin_scatter", "raster_forward", "visibility",
-    "search_radius", "occ_backward", "colour_backward", "zbuf_backward", "chain_world", "grid_2d", "occ_bin"};
+    "search_radius", "occ_backward", "colour_backward", "zbuf_backward", "chain_world", "grid_2d", "occ_bin", "knn"};
 
 // ---------------------------------------------------------------------------------------------
 // Exclusive scan, single pass with decoupled look-back.  Replaces external/prefix_sum

@@ -158,6 +158,21 @@ DSS_API int dss_occ_backward(dss_ctx *ctx, const float *points, const float *rad
 DSS_API int dss_zbuf_backward(dss_ctx *ctx, const int32_t *idx, const float *grad_zbuf, int64_t num_pixels,
                       int K, float *z_grad, void *stream);
 
+/* ---- splat-size K-NN -------------------------------------------
+ * Replaces frnn.frnn_grid_points(points1, points2, lengths1, lengths2, K, r) (external/FRNN/frnn/frnn.py:15-175;
+ * grid.cu:62-99,285-373; counting_sort.cu:5-36), called by DSS with K = 7, r = 0.2 on the world-space cloud to size the
+ * splats (DSS/core/rasterizer.py:313-326, 369-388).  For every query of cloud n: the K points of cloud n with the
+ * smallest (squared distance, index), squared distance < r^2 (r <= 0: no limit), ascending; missing entries are -1.
+ * Semantics and tie rule of the reference's ground truth FRNNBruteForceCPU (bruteforce_cpu.cpp:8-64).
+ * Packed layout: cloud n owns rows [first_idx[n], first_idx[n] + num_points[n]) and the clouds are contiguous
+ * (first_idx[n] = sum of the earlier num_points); idxs are local to the cloud.  queries == NULL (or == points): the
+ * cloud is searched against itself (the self match, distance 0, is returned first, as in the reference).
+ * sq_dists (Pq,K) f32, idxs (Pq,K) i32 or NULL.  1 <= K <= 32.  No host synchronisation. */
+DSS_API int dss_knn_points(dss_ctx *ctx, const float *queries, const int64_t *query_first_idx,
+                           const int64_t *query_num, const float *points, const int64_t *first_idx,
+                           const int64_t *num_points, int N, int64_t Pq, int64_t P, int K, float radius,
+                           float *sq_dists, int32_t *idxs, void *stream);
+
 /* ---- fused renderer path (what bench.py times) ----------------------------------------------
  * One call per direction for SurfaceSplattingRenderer.forward / its autograd backward
  * (DSS/core/renderer.py:36-82, DSS/core/rasterizer.py:584-664,749-977).  All pointers device. */

@@ -221,3 +221,16 @@ def preprocess_f64(M, V, pts, nrm, h, cutoff, sigma, S):
                                 C.c_long(P0), C.c_float(cutoff), C.c_float(sigma), C.c_int(S), _p(ndc),
                                 _p(ell), _p(rad), _p(sc), _p(jac))
     return dict(ndc=ndc, ellipse=ell, radii=rad, scaler=sc, jac=jac)
+
+
+def knn_brute(queries, qfirst, qnum, points, first, num, K, r):
+    """-> (dists (Pq,K) f32 ascending, idxs (Pq,K) i32 local to the cloud), -1 padded.
+    external/FRNN/frnn/csrc/bruteforce/bruteforce_cpu.cpp:8-64."""
+    queries, points = _f32(queries), _f32(points)
+    qfirst, qnum, first, num = _i64(qfirst), _i64(qnum), _i64(first), _i64(num)
+    assert K <= 64
+    d = np.full((queries.shape[0], K), -1, np.float32)
+    i = np.full((queries.shape[0], K), -1, np.int32)
+    lib().oracle_knn_brute(_p(queries), _p(qfirst), _p(qnum), _p(points), _p(first), _p(num), C.c_int(len(num)),
+                           C.c_int(K), C.c_float(r), _p(d), _p(i))
+    return d, i

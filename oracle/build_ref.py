@@ -5,6 +5,7 @@ only to oracle/_ref/ (git-ignored, NOT gpurun-ignored, so the built .so files tr
 On the GPU box /root/reference does not exist: the prebuilt modules are imported as they are.
 
   dss_ref_cpu  : DSS/csrc/rasterize_points_cpu.cpp through oracle/ref_shim_cpu.cpp          (CPU)
+  dss_ref_frnn_cpu : external/FRNN/frnn/csrc/bruteforce/bruteforce_cpu.cpp (K-NN ground truth)   (CPU)
   dss_ref_cuda : DSS/csrc/rasterize_points.cu, rasterize_points_backward.cu,
                  external/prefix_sum/prefix_sum.cu, external/FRNN/frnn/csrc/grid/{grid,counting_sort}.cu
                  through oracle/ref_shim_cuda.cpp, nvcc sm_100a                              (GPU witness)
@@ -90,6 +91,26 @@ def build_prefix_sum(verbose=False):
                 extra_cuda_cflags=["-O3", "-gencode", "arch=compute_100a,code=sm_100a"], verbose=verbose)
 
 
+def build_frnn_cpu(verbose=False):
+    """external/FRNN/frnn/csrc/bruteforce/bruteforce_cpu.cpp through oracle/ref_shim_frnn_cpu.cpp."""
+    srcs = [os.path.join(HERE, "ref_shim_frnn_cpu.cpp"),
+            os.path.join(REF, "external/FRNN/frnn/csrc/bruteforce/bruteforce_cpu.cpp")]
+    if not os.path.isdir(REF) or not _stale("dss_ref_frnn_cpu", srcs):
+        return _load_prebuilt("dss_ref_frnn_cpu")
+    from torch.utils.cpp_extension import load
+    bd = os.path.join(OUT, "dss_ref_frnn_cpu")
+    os.makedirs(bd, exist_ok=True)
+    return load(name="dss_ref_frnn_cpu", sources=srcs, build_directory=bd, extra_cflags=["-O2"], verbose=verbose)
+
+
+def ref_frnn_cpu():
+    try:
+        return build_frnn_cpu()
+    except Exception as e:  # pragma: no cover
+        print("oracle/_ref frnn cpu build failed:", e, file=sys.stderr)
+        return None
+
+
 def ref_cpu():
     """The reference CPU module, or None when neither /root/reference nor a prebuilt .so exists."""
     try:
@@ -116,7 +137,7 @@ def ref_prefix_sum():
 
 
 def build_all(verbose=False):
-    return build_cpu(verbose), build_cuda(verbose), build_prefix_sum(verbose)
+    return build_cpu(verbose), build_cuda(verbose), build_prefix_sum(verbose), build_frnn_cpu(verbose)
 
 
 if __name__ == "__main__":

@@ -597,3 +597,51 @@ ORACLE_API void oracle_preprocess_f64(const float *M, const float *V, const floa
         }
     }
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * K nearest neighbours within a radius -- restates the reference's own ground truth FRNNBruteForceCPU
+ * (external/FRNN/frnn/csrc/bruteforce/bruteforce_cpu.cpp:8-64): per query of cloud n, over the points of the same
+ * cloud, dist = sum_d diff*diff accumulated in dimension order (:41-45); a point qualifies iff dist < r*r (:48,51);
+ * the K smallest (dist, index) tuples are kept (max-heap of tuples, :38,46-54) and written in ascending order, the
+ * rest stays -1 (:22-23,55-61).  Packed layout: cloud n owns rows [first[n], first[n] + num[n]); indices are local to
+ * the cloud.  r <= 0: no radius limit (pytorch3d knn_points, rasterizer.py:308-312).
+ * ------------------------------------------------------------------------------------------- */
+ORACLE_API void oracle_knn_brute(const float *queries, const int64_t *qfirst, const int64_t *qnum, const float *points,
+                                 const int64_t *first, const int64_t *num, int N, int K, float r, float *dists,
+                                 int32_t *idxs) {
+    const float r2 = r > 0 ? r * r : INFINITY;
+    for (int n = 0; n < N; ++n) {
+#pragma omp parallel for schedule(dynamic, 64)
+        for (int64_t a = 0; a < qnum[n]; ++a) {
+            const float *q = queries + (qfirst[n] + a) * 3;
+            float bd[64];
+            int bi[64];
+            int cnt = 0;
+            for (int64_t b = 0; b < num[n]; ++b) {
+                const float *p = points + (first[n] + b) * 3;
+                float dist = 0;
+                for (int d = 0; d < 3; ++d) {
+                    const float diff = q[d] - p[d];
+                    dist += diff * diff;
+                }
+                if (!(dist < r2)) continue;
+                if (cnt == K && !(dist < bd[K - 1])) continue;     /* strict: earlier index wins ties (:51) */
+                int k = cnt < K ? cnt : K - 1;
+                while (k > 0 && (dist < bd[k - 1])) {              /* equal distances keep index order */
+                    bd[k] = bd[k - 1];
+                    bi[k] = bi[k - 1];
+                    --k;
+                }
+                bd[k] = dist;
+                bi[k] = (int)b;
+                if (cnt < K) ++cnt;
+            }
+            float *od = dists + (qfirst[n] + a) * K;
+            int32_t *oi = idxs + (qfirst[n] + a) * K;
+            for (int k = 0; k < K; ++k) {
+                od[k] = k < cnt ? bd[k] : -1.0f;
+                oi[k] = k < cnt ? bi[k] : -1;
+            }
+        }
+    }
+}
