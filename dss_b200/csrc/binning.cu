@@ -45,16 +45,35 @@ int pack_records(dss_ctx *ctx, const float *points, const float *radii, const fl
 // range [lo, hi].  We estimate it arithmetically and fix it up with the exact predicate, which makes
 // the membership bit-identical to the reference's brute-force loop at O(1) cost.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float bin_lo_edge(int b, int bin, int S, float half_pix) {
-    return pix_to_ndc(b * bin, S) - half_pix;
+// (pix_to_ndc_fast: for a power-of-two S the division-free form is bit-identical to the reference's expression,
+//  see common.cuh -- the edges are evaluated up to eight times per splat and axis, the IEEE division dominated the
+//  instruction count of both binning kernels)
+struct EdgeCtx {
+    int bin, S, B;
+    float inv_S, half_pix;
+};
+__device__ __forceinline__ EdgeCtx make_edge_ctx(int bin, int S, int B) {
+    EdgeCtx e;
+    e.bin = bin;
+    e.S = S;
+    e.B = B;
+    e.inv_S = 1.0f / (float)S;
+    e.half_pix = 1.0f / S;
+    return e;
 }
-__device__ __forceinline__ float bin_hi_edge(int b, int bin, int S, float half_pix) {
-    return pix_to_ndc((b + 1) * bin - 1, S) + half_pix;
+template <bool POW2>
+__device__ __forceinline__ float bin_lo_edge(int b, const EdgeCtx &e) {
+    return pix_to_ndc_fast(b * e.bin, e.S, e.inv_S, POW2) - e.half_pix;
+}
+template <bool POW2>
+__device__ __forceinline__ float bin_hi_edge(int b, const EdgeCtx &e) {
+    return pix_to_ndc_fast((b + 1) * e.bin - 1, e.S, e.inv_S, POW2) + e.half_pix;
 }
 
-__device__ __forceinline__ void bin_range(float p0, float p1, int bin, int S, int B, int &lo, int &hi) {
-    const float half_pix = 1.0f / S;
-    const float scale = (float)S / (2.0f * (float)bin);
+template <bool POW2>
+__device__ __forceinline__ void bin_range(float p0, float p1, const EdgeCtx &e, int &lo, int &hi) {
+    const int B = e.B;
+    const float scale = (float)e.S / (2.0f * (float)e.bin);
     // estimates (may be off by one or two; NaN/inf handled by the clamps and the exact fix-up)
     float e0 = floorf((p0 + 1.0f) * scale) - 1.0f;
     float e1 = floorf((p1 + 1.0f) * scale) + 1.0f;
@@ -62,11 +81,11 @@ __device__ __forceinline__ void bin_range(float p0, float p1, int bin, int S, in
     hi = (e1 >= 0.0f) ? ((e1 < (float)B) ? (int)e1 : B - 1) : -1;    // NaN -> -1
     if (hi > B - 1) hi = B - 1;
     // lo = smallest b with p0 <= b1(b)
-    while (lo > 0 && p0 <= bin_hi_edge(lo - 1, bin, S, half_pix)) --lo;
-    while (lo < B && !(p0 <= bin_hi_edge(lo, bin, S, half_pix))) ++lo;
+    while (lo > 0 && p0 <= bin_hi_edge<POW2>(lo - 1, e)) --lo;
+    while (lo < B && !(p0 <= bin_hi_edge<POW2>(lo, e))) ++lo;
     // hi = largest b with b0(b) <= p1
-    while (hi < B - 1 && bin_lo_edge(hi + 1, bin, S, half_pix) <= p1) ++hi;
-    while (hi >= 0 && !(bin_lo_edge(hi, bin, S, half_pix) <= p1)) --hi;
+    while (hi < B - 1 && bin_lo_edge<POW2>(hi + 1, e) <= p1) ++hi;
+    while (hi >= 0 && !(bin_lo_edge<POW2>(hi, e) <= p1)) --hi;
 }
 
 struct BinRect {
@@ -74,6 +93,7 @@ struct BinRect {
     bool empty;
 };
 
+template <bool POW2>
 __device__ __forceinline__ BinRect splat_bin_rect(const float4 A, const float ry, int bin, int S, int B) {
     BinRect r;
     r.empty = true;
@@ -82,9 +102,10 @@ __device__ __forceinline__ BinRect splat_bin_rect(const float4 A, const float ry
     if (A.z < 0) return r;  // behind the camera (rasterize_points.cu:351-352); also NaN-safe below
     const float px0 = A.x - A.w, px1 = A.x + A.w;
     const float py0 = A.y - ry, py1 = A.y + ry;
-    bin_range(py0, py1, bin, S, B, r.y0, r.y1);
+    const EdgeCtx e = make_edge_ctx(bin, S, B);
+    bin_range<POW2>(py0, py1, e, r.y0, r.y1);
     if (r.y0 > r.y1) return r;
-    bin_range(px0, px1, bin, S, B, r.x0, r.x1);
+    bin_range<POW2>(px0, px1, e, r.x0, r.x1);
     if (r.x0 > r.x1) return r;
     r.empty = false;
     return r;
@@ -169,7 +190,7 @@ __device__ __forceinline__ unsigned int pack_rect(const BinRect &r, int slice) {
                          ((unsigned int)slice << 28);
 }
 
-template <bool SMEM>
+template <bool SMEM, bool POW2>
 __global__ void __launch_bounds__(BIN_THREADS)
 bin_count_kernel(const float4 *__restrict__ rec, const int64_t *__restrict__ first_idx,
                  const int64_t *__restrict__ num_points, int64_t P0_shared, int S, int bin, int B, int NS,
@@ -193,7 +214,7 @@ bin_count_kernel(const float4 *__restrict__ rec, const int64_t *__restrict__ fir
         const int64_t p = vr.first + i;
         const float4 A = __ldg(&rec[2 * p]);
         const float ry = __ldg(&rec[2 * p + 1]).x;
-        const BinRect r = splat_bin_rect(A, ry, bin, S, B);
+        const BinRect r = splat_bin_rect<POW2>(A, ry, bin, S, B);
         if (r.empty) continue;
         const int sl = depth_slice(sm, A.z);
         for (int by = r.y0; by <= r.y1; ++by)
@@ -212,7 +233,7 @@ bin_count_kernel(const float4 *__restrict__ rec, const int64_t *__restrict__ fir
 }
 
 // cursors: copy of offsets (N*B*B), advanced atomically; ids: CSR payload.
-template <bool SMEM>
+template <bool SMEM, bool POW2>
 __global__ void __launch_bounds__(BIN_THREADS)
 bin_scatter_kernel(const float4 *__restrict__ rec, const int64_t *__restrict__ first_idx,
                    const int64_t *__restrict__ num_points, int64_t P0_shared, int S, int bin, int B, int NS,
@@ -239,7 +260,7 @@ bin_scatter_kernel(const float4 *__restrict__ rec, const int64_t *__restrict__ f
             const int64_t p = vr.first + i;
             const float4 A = __ldg(&rec[2 * p]);
             const float ry = __ldg(&rec[2 * p + 1]).x;
-            const BinRect r = splat_bin_rect(A, ry, bin, S, B);
+            const BinRect r = splat_bin_rect<POW2>(A, ry, bin, S, B);
             if (!r.empty) {
                 const int sl = depth_slice(sm, A.z);
                 if (SMEM) rect[j] = pack_rect(r, sl);
@@ -312,14 +333,20 @@ int bin_count_and_scan(dss_ctx *ctx, const float4 *rec, const int64_t *first_idx
     DSS_CUDA_TRY(cudaMemsetAsync(counts, 0, (size_t)(nb + 1) * sizeof(int32_t), st));
     if (P0 > 0) {
         dim3 grid((unsigned)((P0 + BIN_CHUNK - 1) / BIN_CHUNK), N);
+        const bool pow2 = (S & (S - 1)) == 0;
         StageScope prof(ctx, ST_BIN_COUNT, st);
         if ((int64_t)B * B * NS <= BIN_MAX_SMEM_TILES && B <= BIN_PACK_MAX_B && NS <= 16 && !ctx->bin_direct) {
             const size_t smem = (size_t)B * B * NS * sizeof(int32_t);
-            int rc = prepare_smem(bin_count_kernel<true>, smem);
+            int rc = pow2 ? prepare_smem(bin_count_kernel<true, true>, smem) : prepare_smem(bin_count_kernel<true, false>, smem);
             if (rc) return rc;
-            bin_count_kernel<true><<<grid, BIN_THREADS, smem, st>>>(rec, first_idx, num_points, P0, S, bin, B, NS, zrange, counts);
+            if (pow2)
+                bin_count_kernel<true, true><<<grid, BIN_THREADS, smem, st>>>(rec, first_idx, num_points, P0, S, bin, B, NS, zrange, counts);
+            else
+                bin_count_kernel<true, false><<<grid, BIN_THREADS, smem, st>>>(rec, first_idx, num_points, P0, S, bin, B, NS, zrange, counts);
+        } else if (pow2) {
+            bin_count_kernel<false, true><<<grid, BIN_THREADS, 0, st>>>(rec, first_idx, num_points, P0, S, bin, B, NS, zrange, counts);
         } else {
-            bin_count_kernel<false><<<grid, BIN_THREADS, 0, st>>>(rec, first_idx, num_points, P0, S, bin, B, NS, zrange, counts);
+            bin_count_kernel<false, false><<<grid, BIN_THREADS, 0, st>>>(rec, first_idx, num_points, P0, S, bin, B, NS, zrange, counts);
         }
         DSS_LAUNCH_CHECK(ctx);
     }
@@ -335,14 +362,20 @@ int bin_scatter(dss_ctx *ctx, const float4 *rec, const int64_t *first_idx, const
     DSS_CUDA_TRY(cudaMemcpyAsync(cursors, offsets, (size_t)nb * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
     if (P0 > 0) {
         dim3 grid((unsigned)((P0 + BIN_CHUNK - 1) / BIN_CHUNK), N);
+        const bool pow2 = (S & (S - 1)) == 0;
         StageScope prof(ctx, ST_BIN_SCATTER, st);
         if ((int64_t)B * B * NS <= BIN_MAX_SMEM_TILES && B <= BIN_PACK_MAX_B && NS <= 16 && !ctx->bin_direct) {
             const size_t smem = (size_t)B * B * NS * sizeof(int32_t);
-            int rc = prepare_smem(bin_scatter_kernel<true>, smem);
+            int rc = pow2 ? prepare_smem(bin_scatter_kernel<true, true>, smem) : prepare_smem(bin_scatter_kernel<true, false>, smem);
             if (rc) return rc;
-            bin_scatter_kernel<true><<<grid, BIN_THREADS, smem, st>>>(rec, first_idx, num_points, P0, S, bin, B, NS, zrange, cursors, ids, cap);
+            if (pow2)
+                bin_scatter_kernel<true, true><<<grid, BIN_THREADS, smem, st>>>(rec, first_idx, num_points, P0, S, bin, B, NS, zrange, cursors, ids, cap);
+            else
+                bin_scatter_kernel<true, false><<<grid, BIN_THREADS, smem, st>>>(rec, first_idx, num_points, P0, S, bin, B, NS, zrange, cursors, ids, cap);
+        } else if (pow2) {
+            bin_scatter_kernel<false, true><<<grid, BIN_THREADS, 0, st>>>(rec, first_idx, num_points, P0, S, bin, B, NS, zrange, cursors, ids, cap);
         } else {
-            bin_scatter_kernel<false><<<grid, BIN_THREADS, 0, st>>>(rec, first_idx, num_points, P0, S, bin, B, NS, zrange, cursors, ids, cap);
+            bin_scatter_kernel<false, false><<<grid, BIN_THREADS, 0, st>>>(rec, first_idx, num_points, P0, S, bin, B, NS, zrange, cursors, ids, cap);
         }
         DSS_LAUNCH_CHECK(ctx);
     }

@@ -422,7 +422,16 @@ raster_sliced_kernel(const __grid_constant__ RasterArgs a) {
         // The tile's list is ordered by depth slice: walk it front to back in chunks of 256 entries.  Every entry at
         // or behind position `base` has z >= slice_bound(slice of base): stop as soon as that cannot enter any list.
         int base = beg, s_cur = 0;
-        int next_id = (base + tid < end) ? a.tile_ids[base + tid] : 0;     // one chunk ahead
+        // software pipeline of the list walk: ids are fetched two chunks ahead, the (gathered) records one chunk ahead,
+        // so that the dependent id -> record loads of a chunk are in flight while the previous chunk is rasterized
+        int id0 = (beg + tid < end) ? a.tile_ids[beg + tid] : -1;
+        int id1 = (beg + RASTER_THREADS + tid < end) ? a.tile_ids[beg + RASTER_THREADS + tid] : -1;
+        float4 pA = make_float4(0.f, 0.f, -1.f, 0.f);
+        float pry = 0.f;
+        if (id0 >= 0) {
+            pA = __ldg(&a.rec[2 * (int64_t)id0]);
+            pry = __ldg(&a.rec[2 * (int64_t)id0 + 1]).x;
+        }
         while (true) {
             bool more = base < end;
             if (more) {
@@ -436,12 +445,17 @@ raster_sliced_kernel(const __grid_constant__ RasterArgs a) {
                 // ---- phase 1: entry-level cull against the block thresholds, survivors -> queue ----
                 const int j = base + tid;
                 bool survive = false;
-                const int id = next_id;
-                if (j + RASTER_THREADS < end) next_id = a.tile_ids[j + RASTER_THREADS];
+                const int id = id0;
+                const float4 A = pA;
+                const float ry = pry;
+                id0 = id1;
+                id1 = (j + 2 * RASTER_THREADS < end) ? a.tile_ids[j + 2 * RASTER_THREADS] : -1;
+                if (id0 >= 0) {
+                    pA = __ldg(&a.rec[2 * (int64_t)id0]);
+                    pry = __ldg(&a.rec[2 * (int64_t)id0 + 1]).x;
+                }
                 if (j < end) {
                     if (STATS) st_scanned++;
-                    const float4 A = __ldg(&a.rec[2 * (int64_t)id]);
-                    const float ry = __ldg(&a.rec[2 * (int64_t)id + 1]).x;
                     if (A.z >= 0.0f) {
                         const int x0 = max(tx0, (int)fmaxf(ceilf((A.x - A.w + 1.0f) * half_S - 0.5f) - 1.0f, -1.0f));
                         const int x1 = min(tx1, (int)fminf(floorf((A.x + A.w + 1.0f) * half_S - 0.5f) + 1.0f, (float)S));

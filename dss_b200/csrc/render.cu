@@ -26,6 +26,19 @@ struct PreArgs {
     int32_t *zrange;   // (N,2) float bits: min / max view depth of the renderable splats, or null
 };
 
+// Fast reciprocal / division / square root (MUFU based, <= 2 ulp): the per-splat quantities are compared with the
+// float64 oracle at 2e-5 .. 2e-3 relative, IEEE-exact division and sqrt were a third of this kernel's instructions.
+__device__ __forceinline__ float fast_rcp(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fast_sqrt(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // Python-side eps helpers of the reference (DSS/utils/mathHelper.py:10-22), zero counts as positive.
 __device__ __forceinline__ float py_eps_denom(float d) { return eps_denom(d, 1e-17f); }
 __device__ __forceinline__ float py_eps_sqrt(float s) { return fmaxf(fabsf(s), 1e-17f); }
@@ -63,7 +76,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const __grid_constant__
         float zv = fmaf(p0, sV[2], fmaf(p1, sV[6], fmaf(p2, sV[10], sV[14])));
         const float te = py_eps_denom(t);
         const float t2 = py_eps_denom(t * t);
-        const float it = 1.0f / te, it2 = 1.0f / t2;
+        const float it = fast_rcp(te), it2 = fast_rcp(t2);
         // J = d(ndc xy)/d(world xyz), 3x2 (Mk = W @ Jk, rasterizer.py:483-494)
         float J0[3], J1[3];
 #pragma unroll
@@ -80,14 +93,15 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const __grid_constant__
         const float hh = a.h_per_splat ? a.h[s] : a.h[n];
         const float G00 = fmaf(hh, T00, aa), G01 = hh * T01, G11 = fmaf(hh, T11, aa);
         const float detG = G00 * G11 - G01 * G01;
-        const float idet = 1.0f / detG;
+        const float idet = fast_rcp(detG);
         const float ea = G11 * idet, eb = -2.0f * G01 * idet, ec = G00 * idet;   // rasterizer.py:543-551
         const float den = py_eps_denom(4.0f * ea * ec - eb * eb);                 // :509-519
-        const float ry = sqrtf(py_eps_sqrt(4.0f * ea * a.cutoffC / den));
-        const float rx = sqrtf(py_eps_sqrt(4.0f * ec * a.cutoffC / den));
+        const float iden = fast_rcp(den);
+        const float ry = fast_sqrt(py_eps_sqrt(4.0f * ea * a.cutoffC * iden));
+        const float rx = fast_sqrt(py_eps_sqrt(4.0f * ec * a.cutoffC * iden));
         const float detT = fmaxf(T00 * T11 - T01 * T01, 0.0f);
-        const float sc = sqrtf(detT) /
-                         py_eps_denom(sqrtf(py_eps_sqrt(detG * (4.0f * CUDART_PI_F * CUDART_PI_F))));  // :558-559
+        const float sc = fast_sqrt(detT) *
+                         fast_rcp(py_eps_denom(fast_sqrt(py_eps_sqrt(detG * (4.0f * CUDART_PI_F * CUDART_PI_F)))));  // :558-559
         // filters (rasterizer.py:187-192, :152): view-space depth range, optional backface
         bool keep = (zv >= a.znear) && (zv <= a.zfar);
         if (a.backface) {
@@ -100,7 +114,8 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const __grid_constant__
             zlo = min(zlo, zb);
             zhi = max(zhi, zb);
         }
-        const float xn = x / t, yn = y / t;
+        const float irt = fast_rcp(t);
+        const float xn = x * irt, yn = y * irt;
         a.rec[2 * s] = make_float4(xn, yn, zv, rx);
         a.rec[2 * s + 1] = make_float4(ry, ea, eb, ec);
         if (a.scaler) a.scaler[s] = sc;

@@ -10,7 +10,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["insert_points_cuda", "counting_sort_cuda", "frnn_grid_points", "knn_points_packed"]
+__all__ = ["insert_points_cuda", "counting_sort_cuda", "frnn_grid_points", "knn_points_packed", "knn_points"]
 
 
 def insert_points_cuda(points, lengths, params, grid_cnt, grid_cell, grid_idx, G):
@@ -109,3 +109,15 @@ def frnn_grid_points(points1, points2, lengths1=None, lengths2=None, K=-1, r=-1,
         nn = torch.gather(points2[:, None].expand(-1, P1, -1, -1), 2, idxs.clamp(min=0)[..., None].expand(-1, -1, -1, 3))
         nn = torch.where((idxs >= 0)[..., None], nn, torch.zeros_like(nn))
     return dists, idxs, nn, None
+
+
+def knn_points(p1, p2, lengths1=None, lengths2=None, K=1, version=-1, return_nn=False, return_sorted=True):
+    """``pytorch3d.ops.knn_points`` [ext, pytorch3d 0.4.0] as DSS calls it (DSS/core/rasterizer.py:308-312 when
+    ``frnn_radius <= 0``; DSS/training/losses.py:157-180 with K = 12): the K nearest neighbours without a radius.
+    Returns ``(dists (N,P1,K), idx (N,P1,K) int64, knn (N,P1,K,3) or None)``; where a cloud has fewer than K points the
+    entries are zero-padded, as pytorch3d documents (not -1 as frnn does)."""
+    dists, idxs, nn, _ = frnn_grid_points(p1, p2, lengths1, lengths2, K=K, r=-1.0, return_nn=return_nn)
+    missing = idxs < 0
+    dists = torch.where(missing, torch.zeros_like(dists), dists)
+    idxs = torch.where(missing, torch.zeros_like(idxs), idxs)
+    return dists, idxs, nn

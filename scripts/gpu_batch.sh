@@ -1,2 +1,3 @@
-python -m pytest tests/test_gpu_fullsize.py tests/test_knn.py -m gpu -q --tb=short 2>&1 | tail -60 > gpurun_out/pytest_new.log
-tail -60 gpurun_out/pytest_new.log | cut -c1-220
+python -m pytest tests -m gpu -x -q --tb=short --durations=8 2>&1 | tail -25 > gpurun_out/pytest.log
+python bench.py --steps 100 > gpurun_out/bench.json 2> gpurun_out/bench.err
+tail -22 gpurun_out/pytest.log | cut -c1-200; python scripts/stage_table.py gpurun_out/bench.json

@@ -157,7 +157,9 @@ def test_occ_backward_matches_oracle(cuda_device, dense):
     out2 = _C._splat_points_occ_fast_cuda_backward(_t(pts[sel], cuda_device), _t(rad[sel], cuda_device),
                                                    _t(rs, cuda_device), _t(g, cuda_device),
                                                    _t(num_v, cuda_device), _t(first_v, cuda_device), None, None)
-    np.testing.assert_array_equal(out2.cpu().numpy(), out[sel])
+    # (the two calls may take different kernels -- staged tile windows vs the direct gather, chosen from the previous
+    #  call's radii -- so compare to rounding, not bit for bit)
+    np.testing.assert_allclose(out2.cpu().numpy(), out[sel], rtol=2e-5, atol=2e-6 * scale)
 
 
 def test_zbuf_backward(cuda_device):

@@ -124,6 +124,13 @@ def test_frnn_grid_points_signature_and_h_rule(cuda_device):
         wd, wi = oracle.knn_brute(x[n, :L], np.zeros(1, np.int64), np.array([L]), x[n, :L], np.zeros(1, np.int64),
                                   np.array([L]), 7, 0.2)
         assert np.array_equal(dists[n, :L].cpu().numpy(), wd) and np.array_equal(idxs[n, :L].cpu().numpy(), wi)
+    # pytorch3d-style twin (no radius, zero padding)
+    from dss_b200.frnn_grid import knn_points
+    kd, ki, _ = knn_points(pts, pts, lens, lens, K=12)
+    wd, wi = oracle.knn_brute(x[1, :1800], np.zeros(1, np.int64), np.array([1800]), x[1, :1800], np.zeros(1, np.int64),
+                              np.array([1800]), 12, -1.0)
+    assert np.array_equal(kd[1, :1800].cpu().numpy(), wd) and np.array_equal(ki[1, :1800].cpu().numpy(), wi)
+    assert (kd[1, 1800:] == 0).all() and (ki[1, 1800:] == 0).all()
     ok = idxs[0] >= 0
     g = torch.gather(pts[0][None].expand(P, -1, -1), 1, idxs[0].clamp(min=0)[..., None].expand(-1, -1, 3))
     assert torch.equal(nn[0][ok], g[ok])
