@@ -277,7 +277,10 @@ def run_ours(a):
     sl = slice(rank * V, (rank + 1) * V)                       # this rank's contiguous slice of the views
     proj_h, view_h = proj_all[sl].contiguous().pin_memory(), view_all[sl].contiguous().pin_memory()
     g = torch.Generator().manual_seed(99 + rank)
-    colours_h = (col.repeat(V, 1) * (0.5 + 0.5 * torch.rand(V * P0, 1, generator=g))).pin_memory()
+    # colours: one RGB per POINT, shared by the views of the step (the quantity an inverse-rendering step optimises
+    # and the one exchange step reduces); per-(view,point) colours -- the layout the reference holds on the device after
+    # shading -- take the same path with a (V*P0,3) tensor (tests/test_gpu_render.py).
+    colours_h = col.contiguous().pin_memory()
     grad_h = (torch.randn(V, S, S, 4, generator=g) * 1e-3).pin_memory()        # dense, like the IoU term
     pts_h, nrm_h = pts.pin_memory(), nrm.pin_memory()
     h_h = torch.full((V,), 5e-5).pin_memory()   # clamp floor of the 6-NN rule at this density (rasterizer.py:326)
@@ -286,7 +289,6 @@ def run_ours(a):
     pts_d = pts_h.to(dev).requires_grad_(True)
     nrm_d, col_d = nrm_h.to(dev), colours_h.to(dev).requires_grad_(True)
     proj_d, view_d, h_d, grad_d = proj_h.to(dev), view_h.to(dev), h_h.to(dev), grad_h.to(dev)
-    grad_sync = torch.zeros(P0, 6, device=dev)     # (d pos, d colour-sum) reduced across ranks when world > 1
 
     def step_resident():
         pts_d.grad = None
@@ -297,9 +299,9 @@ def run_ours(a):
 
     def allreduce_grads():
         # the one exchange step of the path: sum of point gradients over all views
-        grad_sync[:, :3] = pts_d.grad
-        grad_sync[:, 3:] = col_d.grad.view(V, P0, 3).sum(0)
-        dist.all_reduce(grad_sync)
+        buf = torch.cat([pts_d.grad, col_d.grad], 1)      # (P0, 6): d position, d colour
+        dist.all_reduce(buf)
+        return buf
 
     def sync_all():
         torch.cuda.synchronize()
@@ -346,8 +348,7 @@ def run_ours(a):
         # host-side inputs of a step: the cloud (positions, normals, per-point colours), this rank's cameras and the
         # image gradient.  Colours go up once per POINT (P0,3): the reference only materialises per-(view,point)
         # colours on the device (after shading), it never uploads them.
-        pcol_h = col.contiguous().pin_memory()
-        host_in = (pts_h, nrm_h, pcol_h, proj_h, view_h, h_h, grad_h)
+        host_in = (pts_h, nrm_h, colours_h, proj_h, view_h, h_h, grad_h)
         # double-buffered device staging: the H2D copy of step i+1 and the D2H read of step i run on a copy
         # stream while step i / i+1 computes; every step still moves all of its inputs and results
         dev_in = [[torch.empty_like(x, device=dev) for x in host_in] for _ in range(2)]
@@ -396,12 +397,13 @@ def run_ours(a):
             out = render_points(p, d[1], c, d[3], d[4], d[5], prm)
             mark("forward_end", main)
             out.image.backward(d[6])
+            gp, gc = p.grad, c.grad
             if world > 1:
-                # the one exchange step of the path: sum of the point gradients over all ranks' views
-                sync = torch.cat([p.grad, c.grad], 1)
+                # the one exchange step of the path: sum of the point gradients over all ranks' views; the reduced
+                # gradients are what goes back to the host
+                sync = torch.cat([gp, gc], 1)
                 dist.all_reduce(sync)
-                p.grad.copy_(sync[:, :3])
-                c.grad.copy_(sync[:, 3:])
+                gp, gc = sync[:, :3], sync[:, 3:]
             ev_done[slot].record(main)
             mark("compute_end", main)
             with torch.cuda.stream(back_stream):
@@ -412,14 +414,14 @@ def run_ours(a):
                     return
                 mark("d2h_begin", back_stream)
                 img_h.copy_(out.image.detach(), non_blocking=True)
-                gpts_h.copy_(p.grad, non_blocking=True)
-                gcol_h.copy_(c.grad, non_blocking=True)
+                gpts_h.copy_(gp, non_blocking=True)
+                gcol_h.copy_(gc, non_blocking=True)
                 ev_out[slot].record(back_stream)
                 mark("d2h_end", back_stream)
             # no record_stream(): the tensors the read-back reads stay referenced until this slot comes round again, and by
             # then the main stream has waited for ev_out[slot] -- the caching allocator sees a plain same-stream free
             # (record_stream defers reuse unpredictably and costs occasional cudaMalloc/cudaFree stalls of ~15 ms)
-            keep[slot] = (out, p, c)
+            keep[slot] = (out, p, c, gp, gc)
             state["i"] = i + 1
 
         h2d = sum(x.numel() * x.element_size() for x in host_in)
@@ -497,6 +499,7 @@ def run_ours(a):
                    "views_total": V * world, "parallelism": "views sharded %d/GPU + 1 NCCL allreduce of point grads" % V
                    if world > 1 else "single GPU",
                    "l2": "per-step inputs %.0f MB + %.0f MB of splat records exceed the 126 MB L2" % (work_mb, V * P0 * 32 / 1e6),
+                   "colours": "per point (P0,3), shared by the views",
                    "settings": "configs/dss.yml:14-22 (cutoff 1, merge 0.05, K=5, radii_s 5, clip 0.05, sigma 1)"},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
     }

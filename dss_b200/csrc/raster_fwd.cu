@@ -344,7 +344,7 @@ __device__ __forceinline__ void sts_u16(uint32_t addr, unsigned short v) {
     asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
 }
 
-constexpr int RASTER_QCAP = 512;
+constexpr int RASTER_QCAP = 1024;
 constexpr int RASTER_WPEND = 256;   // accepted fragments a warp buffers before it inserts them
 
 // lock-free sorted insert of one key into a pixel's K slots (chain of atomicMin, see above)
