@@ -75,15 +75,12 @@ occ_bin_kernel(const float4 *__restrict__ rec, const uint8_t *__restrict__ visib
     for (int t = threadIdx.x; t < nt; t += 256) s_hist[t] = 0;
     __syncthreads();
     int tile[ITEMS];
-    float4 cr[ITEMS];
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
         tile[j] = -1;
         const int64_t i = chunk0 + j * 256 + threadIdx.x;
         if (i < vr.count && visible[vr.first + i]) {
             const float4 A = __ldg(&rec[2 * (vr.first + i)]);
-            const float ry = __ldg(&rec[2 * (vr.first + i) + 1]).x;
-            cr[j] = make_float4(A.x, A.y, A.w, ry);
             tile[j] = (centre_pixel(A.y, S) / OCC_TILE) * OB + centre_pixel(A.x, S) / OCC_TILE;
             atomicAdd(&s_hist[tile[j]], 1);
         }
@@ -101,12 +98,16 @@ occ_bin_kernel(const float4 *__restrict__ rec, const uint8_t *__restrict__ visib
     }
     if (PASS == 0) return;
     __syncthreads();
+    // (the record is read again here -- an L2 hit -- rather than carried in 32 registers across the two barriers)
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j)
         if (tile[j] >= 0) {
+            const int64_t p = vr.first + chunk0 + j * 256 + threadIdx.x;
+            const float4 A = __ldg(&rec[2 * p]);
+            const float ry = __ldg(&rec[2 * p + 1]).x;
             const int slot = atomicAdd(&s_hist[tile[j]], 1);
-            crec[slot] = cr[j];
-            cids[slot] = (int32_t)(vr.first + chunk0 + j * 256 + threadIdx.x);
+            crec[slot] = make_float4(A.x, A.y, A.w, ry);
+            cids[slot] = (int32_t)p;
         }
 }
 
