@@ -475,8 +475,15 @@ def run_ours(a):
     achieved = alg / (dom_avg_ms * 1e-3) / 1e9 if dom_avg_ms > 0 else 0.0
     step_bytes = V * algorithmic_bytes_per_view(P0, S, K)
     step_gbs = step_bytes / (ms_max / a.steps * 1e-3) / 1e9
+    traffic = None
+    try:    # measured DRAM bytes per launch of this stage's kernel, from the committed ncu --set full capture
+        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        if P0 == 1_000_000 and S == 512 and V == 8 and K == 5:
+            traffic = tr.get(dom)
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "kernel_ms_per_launch": dom_avg_ms, "kernel_share_of_step": dom_ms / total_stage_ms,
                 "stage_ms_per_step": {k: v[0] / a.steps for k, v in stages.items() if v[1]},
                 "whole_step": {"algorithmic_bytes": step_bytes, "achieved": step_gbs, "frac": step_gbs / peak,
