@@ -102,6 +102,7 @@ struct dss_ctx {
     const void *occ_counts_ptr;   // BUF_OCC_COUNTS block known to be all zero (nullptr: unknown)
     size_t occ_counts_elems;
     int ns_override;    // tuning (env DSS_NS): number of depth slices of the forward tile lists, 0 = automatic
+    int occ_tilebin;    // tuning (env DSS_OCC_TILEBIN=1): bin the backward's visible splats by tile only (unordered lists)
     int bin_direct;     // tuning (env DSS_BIN_DIRECT): tile binning with plain global atomics instead of per-block histograms
     double stage_ms[dss::NUM_STAGES];
     int64_t stage_calls[dss::NUM_STAGES];

@@ -111,6 +111,36 @@ occ_bin_kernel(const float4 *__restrict__ rec, const uint8_t *__restrict__ visib
         }
 }
 
+// Cell-level variant: the bins are the PIXELS (32 x 32 cells per tile, cell = tile * 1024 + local pixel), so a tile's
+// compact list comes out ordered by pixel row, then column.  Consecutive splats of a list then sit in the same or the
+// next pixel -- the splats a warp of the tile kernel works on together read (nearly) the same shared-memory rows and
+// columns, which turns its 4-way bank conflicts into broadcasts.  Two million bins per 8 views do not fit a block
+// histogram: plain global atomics (1.5M visible splats over 0.5M occupied cells -- no hot spots).
+template <int PASS>
+__global__ void __launch_bounds__(256)
+occ_cellbin_kernel(const float4 *__restrict__ rec, const uint8_t *__restrict__ visible,
+                   const int64_t *__restrict__ first_idx, const int64_t *__restrict__ num_points, int64_t P0_shared,
+                   int S, int OB, int32_t *__restrict__ counters, const int32_t *__restrict__ offsets,
+                   float4 *__restrict__ crec, int32_t *__restrict__ cids) {
+    const int n = blockIdx.y;
+    const ViewRange vr = view_range(first_idx, num_points, n, P0_shared);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < vr.count; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = vr.first + i;
+        if (!visible[p]) continue;
+        const float4 A = __ldg(&rec[2 * p]);
+        const int cx = centre_pixel(A.x, S), cy = centre_pixel(A.y, S);
+        const int64_t tile = (int64_t)n * OB * OB + (cy / OCC_TILE) * OB + cx / OCC_TILE;
+        const int64_t cell = tile * (OCC_TILE * OCC_TILE) + (cy % OCC_TILE) * OCC_TILE + (cx % OCC_TILE);
+        if (PASS == 0) {
+            atomicAdd(&counters[cell], 1);
+        } else {
+            const int slot = offsets[cell] + atomicSub(&counters[cell], 1) - 1;
+            crec[slot] = make_float4(A.x, A.y, A.w, __ldg(&rec[2 * p + 1]).x);
+            cids[slot] = (int32_t)p;
+        }
+    }
+}
+
 static inline unsigned int occ_nblocks(int64_t items, int threads, int sm_count, int per_sm) {
     int64_t b = (items + threads - 1) / threads;
     const int64_t cap = (int64_t)sm_count * per_sm;
@@ -363,12 +393,12 @@ __host__ __device__ __forceinline__ bool occ_fits(float r, int S, int R_box) {
 }
 
 __global__ void __launch_bounds__(256)
-occ_parts_kernel(const int32_t *__restrict__ tile_offsets, const float *__restrict__ rs, int nt_view, int64_t nt, int S,
-                 int R_box, int32_t *__restrict__ parts) {
+occ_parts_kernel(const int32_t *__restrict__ tile_offsets, int cs, const float *__restrict__ rs, int nt_view, int64_t nt,
+                 int S, int R_box, int32_t *__restrict__ parts) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t > nt) return;
     int p = 0;
-    if (t < nt && occ_fits(rs[t / nt_view], S, R_box)) p = (tile_offsets[t + 1] - tile_offsets[t] + OCC_ITEM - 1) / OCC_ITEM;
+    if (t < nt && occ_fits(rs[t / nt_view], S, R_box)) p = (tile_offsets[(t + 1) * cs] - tile_offsets[t * cs] + OCC_ITEM - 1) / OCC_ITEM;
     parts[t] = p;   // parts[nt] = 0 so that the scan's last entry is the total
 }
 
@@ -382,7 +412,8 @@ occ_items_kernel(const int32_t *__restrict__ part_off, int64_t nt, int32_t *__re
 struct OccTileArgs {
     const float4 *crec;          // compact tile-ordered records {px, py, rx, ry}
     const int32_t *cids;         // packed splat id of every compact record
-    const int32_t *tile_offsets; // (N*OB*OB + 1)
+    const int32_t *tile_offsets; // (N*OB*OB*cs + 1): list of tile t = [tile_offsets[t*cs], tile_offsets[(t+1)*cs])
+    int cs;                      // bins per tile: 1 (tile-level binning) or 1024 (cell-level, lists ordered by pixel)
     const int32_t *part_off;     // (N*OB*OB + 1) exclusive scan of the items per tile; last = number of items
     const int32_t *item_tile;    // tile (n*OB*OB + tile) of every item
     const float *rs;             // (N,) search radius
@@ -529,6 +560,9 @@ __device__ __forceinline__ void occ_item(const OccTileArgs &a, const OccItem &it
 // window buffer when the tile changes, the item's records into the free record buffer), completion signalled on the
 // slot's "full" mbarrier; warps 0-7 are CONSUMERS -- they wait on "full", gather, and release the slot through its
 // "empty" mbarrier.  Two item slots and two window buffers are in flight, so staging overlaps the arithmetic.
+// (Measured alternatives, all slower on the bench workload: 10 consumer warps at 80 registers (+20 %, spills);
+//  12 consumer warps with at most 2 column pairs per lane, 70 registers (+23 %: 4 instead of 8 splats share the per-row
+//  instructions); 8 lanes x 2 pairs per splat at 96 registers (+10 %).)
 template <bool POW2, int NCONS>
 __global__ void __launch_bounds__((NCONS + 1) * 32, 2)
 occ_tile_kernel(const __grid_constant__ OccTileArgs a) {
@@ -592,7 +626,7 @@ occ_tile_kernel(const __grid_constant__ OccTileArgs a) {
             const int n = t / (OB * OB), tile = t - n * OB * OB;
             const int ty = tile / OB, tx = tile - ty * OB;
             const int p = item - a.part_off[t], parts = a.part_off[t + 1] - a.part_off[t];
-            const int tb = a.tile_offsets[t], count = a.tile_offsets[t + 1] - tb;
+            const int tb = a.tile_offsets[(int64_t)t * a.cs], count = a.tile_offsets[(int64_t)(t + 1) * a.cs] - tb;
             const int per = (count + parts - 1) / parts;
             const int beg = tb + p * per;
             const int cnt = max(0, min(count - p * per, per));
@@ -800,30 +834,44 @@ int occ_backward(dss_ctx *ctx, const float4 *rec, const uint8_t *visible, float 
         float4 *crec = nullptr;
         float *planes = nullptr;
         const int PAD = R_box, W = OB * OCC_TILE + 2 * PAD, Hp = W;
-        if ((rc = ctx_get(ctx, BUF_OCC_COUNTS, (size_t)(nt + 1), &counts))) return rc;
-        if ((rc = ctx_get(ctx, BUF_TILE_OFFSETS, (size_t)(nt + 1), &offsets))) return rc;
+        // bins: pixels (lists ordered by pixel inside a tile) unless that needs more than 32M counters
+        const int cs = (!ctx->occ_tilebin && nt * (OCC_TILE * OCC_TILE) <= ((int64_t)32 << 20)) ? OCC_TILE * OCC_TILE : 1;
+        const int64_t nc = nt * cs;
+        if ((rc = ctx_get(ctx, BUF_OCC_COUNTS, (size_t)(nc + 1), &counts))) return rc;
+        if ((rc = ctx_get(ctx, BUF_TILE_OFFSETS, (size_t)(nc + 1), &offsets))) return rc;
         if ((rc = ctx_get(ctx, BUF_OCC_IDS, (size_t)(Ptot > 0 ? Ptot : 1), &cids))) return rc;
         if ((rc = ctx_get(ctx, BUF_OCC_REC, (size_t)(Ptot > 0 ? Ptot : 1), &crec))) return rc;
         if ((rc = ctx_get(ctx, BUF_OCC_PLANES, (size_t)N * 2 * Hp * W, &planes))) return rc;
         {
             StageScope prof(ctx, ST_OCC_BIN, st);
-            // the per-tile counters live in their own buffer and are left at zero by every successful call
-            const bool clean = ctx->occ_counts_ptr == counts && ctx->occ_counts_elems >= (size_t)(nt + 1);
+            // the counters live in their own buffer and are left at zero by every successful call
+            const bool clean = ctx->occ_counts_ptr == counts && ctx->occ_counts_elems >= (size_t)(nc + 1);
             ctx->occ_counts_ptr = nullptr;   // restored below; an error in between forces the memset next time
             if (!clean) DSS_CUDA_TRY(cudaMemsetAsync(counts, 0, ctx->cap[BUF_OCC_COUNTS], st));
-            dim3 bgrid((unsigned)((P0 + 2047) / 2048), N);
-            const size_t hist = (size_t)OB * OB * sizeof(int32_t);
-            if (hist > 48 * 1024) {
-                DSS_CUDA_TRY(cudaFuncSetAttribute(occ_bin_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist));
-                DSS_CUDA_TRY(cudaFuncSetAttribute(occ_bin_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist));
+            if (cs == 1) {
+                dim3 bgrid((unsigned)((P0 + 2047) / 2048), N);
+                const size_t hist = (size_t)OB * OB * sizeof(int32_t);
+                if (hist > 48 * 1024) {
+                    DSS_CUDA_TRY(cudaFuncSetAttribute(occ_bin_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist));
+                    DSS_CUDA_TRY(cudaFuncSetAttribute(occ_bin_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist));
+                }
+                occ_bin_kernel<0><<<bgrid, 256, hist, st>>>(rec, visible, first_idx, num_points, P0, S, OB, counts, nullptr,
+                                                            nullptr, nullptr);
+                DSS_LAUNCH_CHECK(ctx);
+                if ((rc = exclusive_scan_i32(ctx, counts, offsets, nc + 1, st))) return rc;
+                occ_bin_kernel<1><<<bgrid, 256, hist, st>>>(rec, visible, first_idx, num_points, P0, S, OB, counts, offsets,
+                                                            crec, cids);
+                DSS_LAUNCH_CHECK(ctx);
+            } else {
+                dim3 bgrid(occ_nblocks(P0, 256 * 4, ctx->sm_count, 8), N);
+                occ_cellbin_kernel<0><<<bgrid, 256, 0, st>>>(rec, visible, first_idx, num_points, P0, S, OB, counts, nullptr,
+                                                             nullptr, nullptr);
+                DSS_LAUNCH_CHECK(ctx);
+                if ((rc = exclusive_scan_i32(ctx, counts, offsets, nc + 1, st))) return rc;
+                occ_cellbin_kernel<1><<<bgrid, 256, 0, st>>>(rec, visible, first_idx, num_points, P0, S, OB, counts, offsets,
+                                                             crec, cids);
+                DSS_LAUNCH_CHECK(ctx);
             }
-            occ_bin_kernel<0><<<bgrid, 256, hist, st>>>(rec, visible, first_idx, num_points, P0, S, OB, counts, nullptr, nullptr,
-                                                        nullptr);
-            DSS_LAUNCH_CHECK(ctx);
-            if ((rc = exclusive_scan_i32(ctx, counts, offsets, nt + 1, st))) return rc;
-            occ_bin_kernel<1><<<bgrid, 256, hist, st>>>(rec, visible, first_idx, num_points, P0, S, OB, counts, offsets, crec,
-                                                        cids);
-            DSS_LAUNCH_CHECK(ctx);
             ctx->occ_counts_ptr = counts;
             ctx->occ_counts_elems = ctx->cap[BUF_OCC_COUNTS] / sizeof(int32_t);
         }
@@ -834,7 +882,7 @@ int occ_backward(dss_ctx *ctx, const float4 *rec, const uint8_t *visible, float 
             DSS_CUDA_TRY(cudaMemsetAsync(hist, 0, (size_t)N * 4 * 256 * sizeof(unsigned int), st));
             dim3 grid(occ_nblocks(P0 / 4 + 1, 256, ctx->sm_count, 1), N);
             for (int pass = 0; pass < 4; ++pass) {
-                select_hist_compact_kernel<<<grid, 256, 0, st>>>(crec, offsets, OB * OB, pass, hist);
+                select_hist_compact_kernel<<<grid, 256, 0, st>>>(crec, offsets, OB * OB * cs, pass, hist);
                 DSS_LAUNCH_CHECK(ctx);
             }
             select_final_kernel<<<N, 32, 0, st>>>(hist, radii_s, rs);
@@ -852,7 +900,7 @@ int occ_backward(dss_ctx *ctx, const float4 *rec, const uint8_t *visible, float 
         if ((rc = ctx_get(ctx, BUF_OCC_PARTS, (size_t)(2 * (nt + 1)), &parts))) return rc;
         if ((rc = ctx_get(ctx, BUF_OCC_ITEMS, (size_t)max_items, &item_tile))) return rc;
         int32_t *part_off = parts + (nt + 1);
-        occ_parts_kernel<<<(unsigned)((nt + 1 + 255) / 256), 256, 0, st>>>(offsets, rs, OB * OB, nt, S, R_box, parts);
+        occ_parts_kernel<<<(unsigned)((nt + 1 + 255) / 256), 256, 0, st>>>(offsets, cs, rs, OB * OB, nt, S, R_box, parts);
         DSS_LAUNCH_CHECK(ctx);
         if ((rc = exclusive_scan_i32(ctx, parts, part_off, nt + 1, st))) return rc;
         occ_items_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(part_off, nt, item_tile);
@@ -861,6 +909,7 @@ int occ_backward(dss_ctx *ctx, const float4 *rec, const uint8_t *visible, float 
         a.crec = crec;
         a.cids = cids;
         a.tile_offsets = offsets;
+        a.cs = cs;
         a.part_off = part_off;
         a.item_tile = item_tile;
         a.rs = rs;
@@ -886,7 +935,7 @@ int occ_backward(dss_ctx *ctx, const float4 *rec, const uint8_t *visible, float 
             kern<<<tgrid, threads, smem, st>>>(a);
             return DSS_OK;
         };
-        // 8 consumer warps + 1 producer warp per CTA (10 consumers measured 20 % slower: 80 registers spill)
+        // 8 consumer warps + 1 producer warp per CTA
         rc = pow2 ? launch(occ_tile_kernel<true, 8>, 9 * 32) : launch(occ_tile_kernel<false, 8>, 9 * 32);
         if (rc) return rc;
         DSS_LAUNCH_CHECK(ctx);
