@@ -1,4 +1,4 @@
-python -m pytest tests -m gpu -x -q --tb=short 2>&1 | tail -5 > gpurun_out/pytest.log
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
-python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err
-tail -3 gpurun_out/pytest.log | cut -c1-200; tail -1 gpurun_out/smoke.log; python scripts/stage_table.py gpurun_out/bench.json; tail -2 gpurun_out/bench.err
+timeout 420 compute-sanitizer --tool initcheck --error-exitcode 99 --print-limit 15 python -m pytest tests/test_gpu_render.py tests/test_knn.py tests/test_gpu_ops.py -m gpu -q -x -k "test_render_backward_matches_oracle or test_render_forward_matches_oracle or ragged_batches or test_occ_backward_matches_oracle or test_splat_points_matches_oracle" > gpurun_out/initcheck.log 2>&1
+echo "initcheck exit $?" >> gpurun_out/initcheck.log
+grep -E "ERROR SUMMARY|Uninitialized|exit|passed|failed" gpurun_out/initcheck.log | head -20
+grep -A12 "Uninitialized" gpurun_out/initcheck.log | head -60

@@ -152,15 +152,16 @@ def test_compositor_matches_oracle_blend():
     np.testing.assert_allclose(img.numpy(), want[..., :3], rtol=1e-5, atol=1e-6)
 
 
-def test_knn_matches_bruteforce():
+def test_knn_is_cuda_only_and_fails_loudly_on_cpu():
+    """the splat-size K-NN has no CPU path either (tests/test_knn.py covers the kernel and the oracle)."""
+    from dss_b200.frnn_grid import frnn_grid_points, knn_points_packed
     pts = torch.rand(300, 3, generator=torch.Generator().manual_seed(0))
-    d2 = knn_sq_dists(pts, K=7, radius=-1, chunk=64)
-    full = ((pts[:, None] - pts[None]) ** 2).sum(-1)
-    want = torch.sort(full, dim=1)[0][:, :7]
-    torch.testing.assert_close(d2, want, rtol=1e-4, atol=1e-6)
-    assert (d2[:, 0].abs() < 1e-6).all()
-    r = knn_sq_dists(pts, K=7, radius=0.05)
-    assert ((r == -1) | (r <= 0.05 ** 2 + 1e-9)).all()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        knn_sq_dists(pts, K=7, radius=0.2)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        knn_points_packed(pts, torch.zeros(1, dtype=torch.int64), torch.full((1,), 300, dtype=torch.int64), 7, 0.2)
+    with pytest.raises(RuntimeError):
+        frnn_grid_points(pts[None], pts[None], K=7, r=0.2)
 
 
 def test_shard_views_partitions_contiguously():
