@@ -211,3 +211,31 @@ def test_grid_insert_and_counting_sort(cuda_device):
         assert np.array_equal(np.sort(si[n, :L]), np.arange(L))
         assert np.array_equal(sp[n, :L], pts[n][si[n, :L]])
         assert (np.diff(wcell[n][si[n, :L]]) >= 0).all()      # cells ascending
+
+
+@pytest.mark.parametrize("S,P,rad_px,expect", [
+    (96, 3000, (0.8, 4.0), "4 lanes/splat, table-driven rows (S not a power of two)"),
+    (256, 6000, (2.0, 5.0), "8 lanes x 3 pairs"),
+    (200, 5000, (4.0, 7.0), "8 lanes x 4 pairs, S not a power of two"),
+    (256, 5000, (6.0, 9.0), "16 lanes x 3 pairs"),
+    (256, 3000, (9.0, 13.0), "window larger than the staged box: direct gather"),
+])
+def test_occ_backward_window_variants(cuda_device, S, P, rad_px, expect):
+    """every lane mapping of the tile kernel (the window width follows the search radius), power-of-two and other image
+    sizes, and the direct-gather kernel for windows that do not fit -- each against the float64 oracle.  The staged box
+    is sized from the previous call's radii, so the first call of a size may take the direct gather and the second the
+    tile kernel: both must be right."""
+    from dss_b200 import _C
+    N, K = 2, 5
+    pts, ell, cut, rad, first, num = random_screen_splats(P, N, S, seed=S + P, rad_px=rad_px)
+    widx, _, _, _ = oracle.splat_points_naive(pts, ell, cut, rad, first, num, 0.05, S, K, fma_mode=1)
+    vis = oracle.visibility(widx, P)
+    rs = oracle.search_radius(rad, vis, first, num, 5.0)
+    g = (np.random.default_rng(S).standard_normal((N, S, S)) * 1e-3).astype(np.float32)
+    g32, g64 = oracle.occ_backward_fast(pts, rad, vis, rs, g, first, num)
+    scale = np.abs(g64).max()
+    args = [_t(x, cuda_device) for x in (pts, rad, vis, rs, g, first, num)]
+    for attempt in range(2):
+        out = _C.occ_backward(*args).cpu().numpy()
+        assert np.abs(out - g64).max() <= 2e-5 * scale + 1e-9, (expect, attempt, np.abs(out - g64).max() / scale)
+        assert (out[vis == 0] == 0).all()
