@@ -61,6 +61,7 @@ enum BufId {
     BUF_OCC_ITEMS,    // tile of every work item
     BUF_OCC_COUNTS,   // per-tile counters of the occupancy binning (kept at zero between calls)
     BUF_OCC_IDS,      // packed splat id of every compact record
+    BUF_TILE_ORDER,   // launch order of the forward tiles
     BUF_KNN_COUNTS,   // 3-D grid of the K-NN search: points per cell
     BUF_KNN_OFFSETS,  //   exclusive scan of the counts
     BUF_KNN_SORTED,   //   points in cell order {x, y, z, index}
@@ -102,6 +103,7 @@ struct dss_ctx {
     const void *occ_counts_ptr;   // BUF_OCC_COUNTS block known to be all zero (nullptr: unknown)
     size_t occ_counts_elems;
     int ns_override;    // tuning (env DSS_NS): number of depth slices of the forward tile lists, 0 = automatic
+    int no_tile_order;  // tuning (env DSS_NO_TILE_ORDER=1): launch the raster tiles in index order
     int occ_tilebin;    // tuning (env DSS_OCC_TILEBIN=1): bin the backward's visible splats by tile only (unordered lists)
     int bin_direct;     // tuning (env DSS_BIN_DIRECT): tile binning with plain global atomics instead of per-block histograms
     double stage_ms[dss::NUM_STAGES];

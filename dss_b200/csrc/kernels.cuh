@@ -68,6 +68,7 @@ struct RasterArgs {
     float cutoff_uniform;
     const int32_t *tile_offsets;  // (N*B*B + 1)
     const int32_t *tile_ids;
+    const int32_t *tile_order;    // launch order of the tiles (longest lists first) or nullptr: block b = tile b
     int ids_capacity;             // entries tile_ids can hold (lists are clamped to it, see bin_and_raster)
     int N, S, K, B;
     int NS;                       // depth slices per tile list

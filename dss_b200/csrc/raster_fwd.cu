@@ -373,6 +373,33 @@ __device__ __forceinline__ void pend_flush(unsigned long long *s_keys, const uns
     __syncwarp();
 }
 
+// Launch order of the tiles: longest lists first (a counting sort of the tiles by the power of two of their list
+// length, one block).  CTAs are handed out in block-index order, so without this the last wave of a launch is whatever
+// tiles happen to come last -- often dense ones, with most SMs already idle.
+__global__ void __launch_bounds__(1024)
+raster_tile_order_kernel(const int32_t *__restrict__ tile_offsets, int NS, int ntiles, int32_t *__restrict__ order) {
+    __shared__ int s_cnt[32], s_base[32];
+    if (threadIdx.x < 32) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    for (int t = threadIdx.x; t < ntiles; t += blockDim.x) {
+        const int len = tile_offsets[(int64_t)(t + 1) * NS] - tile_offsets[(int64_t)t * NS];
+        atomicAdd(&s_cnt[len > 0 ? 31 - __clz(len) + 1 : 0], 1);      // bucket 0: empty, k: 2^(k-1) <= len < 2^k
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int b = 31; b >= 0; --b) {   // descending work
+            s_base[b] = run;
+            run += s_cnt[b];
+        }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < ntiles; t += blockDim.x) {
+        const int len = tile_offsets[(int64_t)(t + 1) * NS] - tile_offsets[(int64_t)t * NS];
+        order[atomicAdd(&s_base[len > 0 ? 31 - __clz(len) + 1 : 0], 1)] = t;
+    }
+}
+
 template <int KMAX, bool PER_POINT_CUTOFF, bool BLEND, bool STATS, int MINB>
 __global__ void __launch_bounds__(RASTER_THREADS, MINB)
 raster_sliced_kernel(const __grid_constant__ RasterArgs a) {
@@ -386,8 +413,9 @@ raster_sliced_kernel(const __grid_constant__ RasterArgs a) {
     __shared__ unsigned int s_tilemax;
 
     const int S = a.S, B = a.B, NS = a.NS;
-    const int n = blockIdx.y;
-    const int tile = blockIdx.x;
+    const int gt = a.tile_order ? a.tile_order[blockIdx.x] : (int)blockIdx.x;   // global tile: view * B*B + tile
+    const int n = gt / (B * B);
+    const int tile = gt - n * B * B;
     const int ty = tile / B, tx = tile - ty * B;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t tb = ((int64_t)n * B * B + tile) * NS;
@@ -584,9 +612,20 @@ raster_sliced_kernel(const __grid_constant__ RasterArgs a) {
 
 
 template <int KMAX>
-static int launch_scatter(dss_ctx *ctx, const RasterArgs &a, cudaStream_t st) {
-    dim3 grid((unsigned)(a.B * a.B), (unsigned)a.N);
+static int launch_scatter(dss_ctx *ctx, const RasterArgs &a_in, cudaStream_t st) {
+    RasterArgs a = a_in;
+    const int ntiles = a.B * a.B * a.N;
+    dim3 grid((unsigned)ntiles);
     StageScope prof(ctx, ST_RASTER_FWD, st);
+    a.tile_order = nullptr;
+    if (!ctx->no_tile_order && ntiles > 4 * ctx->sm_count) {
+        int32_t *order = nullptr;
+        int rc = ctx_get(ctx, BUF_TILE_ORDER, (size_t)ntiles, &order);
+        if (rc) return rc;
+        raster_tile_order_kernel<<<1, 1024, 0, st>>>(a.tile_offsets, a.NS, ntiles, order);
+        DSS_LAUNCH_CHECK(ctx);
+        a.tile_order = order;
+    }
     const bool blend = a.image != nullptr;
     if (a.stats) {   // debug counters on: one generic instantiation is enough
         if (blend) raster_sliced_kernel<KMAX, true, true, true, 4><<<grid, RASTER_THREADS, 0, st>>>(a);
