@@ -416,6 +416,7 @@ struct OccTileArgs {
     int cs;                      // bins per tile: 1 (tile-level binning) or 1024 (cell-level, lists ordered by pixel)
     const int32_t *part_off;     // (N*OB*OB + 1) exclusive scan of the items per tile; last = number of items
     const int32_t *item_tile;    // tile (n*OB*OB + tile) of every item
+    int *group_counter;          // next group of items to hand out (zero at launch)
     const float *rs;             // (N,) search radius
     const float *planes;         // (N, 2, Hp, W)
     float2 *grad_xy;             // (P,) out
@@ -596,21 +597,30 @@ occ_tile_kernel(const __grid_constant__ OccTileArgs a) {
 
     const int n_items = a.part_off[a.nt];
     const int n_groups = (n_items + OCC_GROUP - 1) / OCC_GROUP;
-    const int my_groups = ((int)blockIdx.x < n_groups) ? (n_groups - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-    // sequence number q of this CTA's items: group = blockIdx.x + (q / OCC_GROUP) * gridDim.x, item = group*G + q%G
-    const int q_end = my_groups * OCC_GROUP;
 
     if (warp == NCONS) {
         // ------------------------------- producer -------------------------------
+        // Groups of OCC_GROUP consecutive items are handed out dynamically (one atomic per group): the views differ
+        // up to 3x in cost per splat (window area), a static round-robin leaves CTAs idle at the end of the launch.
         int wt_cur = -1;                       // tile held by the current window buffer
         int wcur = 0;
         int slot_use = 0;                      // items staged so far
-        for (int q = 0; q <= q_end; ++q) {
+        int group = -1, k_in = OCC_GROUP;      // current group, next item inside it
+        for (;;) {
             const int slot = slot_use & 1;
+            if (k_in >= OCC_GROUP) {
+                if (lane == 0) group = atomicAdd(a.group_counter, 1);
+                group = __shfl_sync(0xffffffffu, group, 0);
+                k_in = 0;
+            }
             int item = -1;
-            if (q < q_end) {
-                item = ((int)blockIdx.x + (q / OCC_GROUP) * (int)gridDim.x) * OCC_GROUP + (q % OCC_GROUP);
-                if (item >= n_items) continue;
+            if (group < n_groups) {
+                item = group * OCC_GROUP + k_in;
+                ++k_in;
+                if (item >= n_items) {      // tail of the last group
+                    k_in = OCC_GROUP;
+                    continue;
+                }
             }
             // wait until the consumers have released this slot (its previous use)
             if (slot_use >= 2) mbar_wait(bar_empty + 8 * slot, (uint32_t)(((slot_use >> 1) - 1) & 1));
@@ -897,7 +907,7 @@ int occ_backward(dss_ctx *ctx, const float4 *rec, const uint8_t *visible, float 
         // work items: parts per tile -> scan -> tile of every item
         int32_t *parts = nullptr, *item_tile = nullptr;
         const int64_t max_items = Ptot / OCC_ITEM + nt + 1;
-        if ((rc = ctx_get(ctx, BUF_OCC_PARTS, (size_t)(2 * (nt + 1)), &parts))) return rc;
+        if ((rc = ctx_get(ctx, BUF_OCC_PARTS, (size_t)(2 * (nt + 1) + 4), &parts))) return rc;
         if ((rc = ctx_get(ctx, BUF_OCC_ITEMS, (size_t)max_items, &item_tile))) return rc;
         int32_t *part_off = parts + (nt + 1);
         occ_parts_kernel<<<(unsigned)((nt + 1 + 255) / 256), 256, 0, st>>>(offsets, cs, rs, OB * OB, nt, S, R_box, parts);
@@ -912,6 +922,8 @@ int occ_backward(dss_ctx *ctx, const float4 *rec, const uint8_t *visible, float 
         a.cs = cs;
         a.part_off = part_off;
         a.item_tile = item_tile;
+        a.group_counter = parts + 2 * (nt + 1);
+        DSS_CUDA_TRY(cudaMemsetAsync(a.group_counter, 0, sizeof(int), st));
         a.rs = rs;
         a.planes = planes;
         a.grad_xy = reinterpret_cast<float2 *>(grad_xy);
