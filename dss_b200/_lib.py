@@ -55,6 +55,7 @@ _SIGNATURES = {
     "dss_profile_stage_name": (C.c_char_p, [C.c_int]),
     "dss_profile_read": (C.c_int, [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "dss_debug_raster_stats": (C.c_int, [vp, C.c_int, C.POINTER(C.c_uint64)]),
+    "dss_debug_limit_tile_capacity": (C.c_int, [vp, C.c_int64]),
     "dss_exclusive_scan_i32": (C.c_int, [vp, vp, vp, C.c_int64, vp]),
     "dss_grid_insert_points_2d": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
     "dss_grid_counting_sort_2d": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
@@ -159,8 +160,14 @@ def raster_stats(enable, device=None):
     """debug counters of the sliced rasterizer accumulated since they were last enabled (see the header)."""
     out = (C.c_uint64 * 8)()
     check(load().dss_debug_raster_stats(ctx(device), int(bool(enable)), out), "dss_debug_raster_stats")
-    names = ["entries_scanned", "survivors", "pixel_tests", "accepted", "slices_skipped", "slices_visited"]
-    return dict(zip(names, [int(v) for v in out[:6]]))
+    names = ["entries_scanned", "survivors", "pixel_tests", "accepted", "entries_sorted", "groups_visited",
+             "overflow_tiles"]
+    return dict(zip(names, [int(v) for v in out[:7]]))
+
+
+def limit_tile_capacity(max_entries, device=None):
+    """testing: cap the forward's tile-list buffer (0 = no cap) so that the overflow path runs (see the header)."""
+    check(load().dss_debug_limit_tile_capacity(ctx(device), int(max_entries)), "dss_debug_limit_tile_capacity")
 
 
 def scratch_bytes(device=None):
