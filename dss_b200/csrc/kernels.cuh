@@ -77,6 +77,7 @@ struct RasterArgs {
     int64_t P0;
     int N, S, K, B;
     int NS;                       // depth slices per tile list
+    int flush_min;                // survivors that trigger a rasterization phase while an ordered list is walked
     const float *zrange;          // (N,2) depth range per view (NS > 1)
     float depth_merge;
     // outputs
@@ -93,6 +94,7 @@ struct RasterArgs {
     uint8_t *visible;      // (P,) must be zeroed by the caller
     int64_t visible_count; // P (to re-zero `visible` when a pass has to be repeated)
     int force_pixel_parallel;  // testing: use the pixel-parallel kernel even for K <= 8
+    uint4 *tile_dbg;           // optional per-tile debug records (with stats)
     unsigned long long *stats; // optional debug counters (dss_debug_raster_stats) or nullptr
 };
 

@@ -446,7 +446,7 @@ template <int LPS, int PPL, bool CENTRE, bool POW2>
 __device__ __forceinline__ void occ_rows(int j0, int j1, const float *__restrict__ gm, const float *__restrict__ gp,
                                          const float *__restrict__ yf_tab, const int side, float2 &yf2,
                                          const float2 pix2, const float2 npy2, const float ry, const float r2,
-                                         const float2 (&dxsq)[PPL], const float2 (&cmask)[PPL], float2 (&sw)[PPL],
+                                         const float2 (&dx2)[PPL], const float2 (&cmask)[PPL], float2 (&sw)[PPL],
                                          float2 (&swy)[PPL]) {
     gm += j0 * side;
     gp += j0 * side;
@@ -458,6 +458,9 @@ __device__ __forceinline__ void occ_rows(int j0, int j1, const float *__restrict
             yf2 = make_float2(yf, yf);
         }
         const float2 dy2 = __fadd2_rn(yf2, npy2);
+        // dist2 = dx*dx + dy*dy as the reference's kernel evaluates it (nvcc: FMUL dy*dy, then FFMA dx*dx + that --
+        // checked in the SASS of rasterize_points_backward.cu:150): the same rounding, hence the same disc membership
+        const float2 dysq2 = __fmul2_rn(dy2, dy2);
         float2 rowm2 = make_float2(0.f, 0.f);
         if (CENTRE) {
             const float m = set_le(fabsf(dy2.x), ry);
@@ -466,7 +469,7 @@ __device__ __forceinline__ void occ_rows(int j0, int j1, const float *__restrict
 #pragma unroll
         for (int s = 0; s < PPL; ++s) {
             float2 g = *reinterpret_cast<const float2 *>(gm + s * 2 * LPS);
-            const float2 d2 = __ffma2_rn(dy2, dy2, dxsq[s]);                    // dy*dy + dx*dx
+            const float2 d2 = __ffma2_rn(dx2[s], dx2[s], dysq2);                // fma(dx, dx, dy*dy)
             const float2 in = make_float2(set_le(d2.x, r2), set_le(d2.y, r2));   // rasterize_points_backward.cu:156
             float2 dc = d2;
             if (CENTRE) {
@@ -519,13 +522,13 @@ __device__ __forceinline__ void occ_item(const OccTileArgs &a, const OccItem &it
         bh = max(__reduce_max_sync(FULL, bh), min(Hh, 1));
         const int jc0 = Hh - bh, jc1 = Hh + bh + 1;
         const float2 npy2 = make_float2(-py, -py);
-        float2 dxsq[PPL], cmask[PPL], sw[PPL], swy[PPL];
+        float2 dx2[PPL], cmask[PPL], sw[PPL], swy[PPL];
         const float *xfp = s_xf + ox + 2 * gl;
 #pragma unroll
         for (int s = 0; s < PPL; ++s) {
             const float2 xf = *reinterpret_cast<const float2 *>(xfp + s * 2 * LPS);
             const float dx0 = xf.x - px, dx1 = xf.y - px;
-            dxsq[s] = make_float2(dx0 * dx0, dx1 * dx1);
+            dx2[s] = make_float2(dx0, dx1);
             cmask[s] = make_float2(set_le(fabsf(dx0), rx), set_le(fabsf(dx1), rx));
             sw[s] = make_float2(0.f, 0.f);
             swy[s] = make_float2(0.f, 0.f);
@@ -533,17 +536,16 @@ __device__ __forceinline__ void occ_item(const OccTileArgs &a, const OccItem &it
         const float yfm1 = s_yf[oy] - pixf;                  // row -1 (POW2: exact)
         float2 yf2 = make_float2(yfm1, yfm1);
         const int off = oy * side + ox + 2 * gl;
-        occ_rows<LPS, PPL, false, POW2>(0, jc0, s_gm + off, s_gp + off, s_yf + oy, side, yf2, pix2, npy2, ry, r2, dxsq, cmask,
+        occ_rows<LPS, PPL, false, POW2>(0, jc0, s_gm + off, s_gp + off, s_yf + oy, side, yf2, pix2, npy2, ry, r2, dx2, cmask,
                                         sw, swy);
-        occ_rows<LPS, PPL, true, POW2>(jc0, jc1, s_gm + off, s_gp + off, s_yf + oy, side, yf2, pix2, npy2, ry, r2, dxsq, cmask,
+        occ_rows<LPS, PPL, true, POW2>(jc0, jc1, s_gm + off, s_gp + off, s_yf + oy, side, yf2, pix2, npy2, ry, r2, dx2, cmask,
                                        sw, swy);
-        occ_rows<LPS, PPL, false, POW2>(jc1, Wwin, s_gm + off, s_gp + off, s_yf + oy, side, yf2, pix2, npy2, ry, r2, dxsq, cmask,
+        occ_rows<LPS, PPL, false, POW2>(jc1, Wwin, s_gm + off, s_gp + off, s_yf + oy, side, yf2, pix2, npy2, ry, r2, dx2, cmask,
                                         sw, swy);
         float gx = 0.f, gy = 0.f;
 #pragma unroll
         for (int s = 0; s < PPL; ++s) {
-            const float2 xf = *reinterpret_cast<const float2 *>(xfp + s * 2 * LPS);
-            gx = fmaf(xf.x - px, sw[s].x, fmaf(xf.y - px, sw[s].y, gx));   // sum_rows dx*w = dx * sum_rows w
+            gx = fmaf(dx2[s].x, sw[s].x, fmaf(dx2[s].y, sw[s].y, gx));     // sum_rows dx*w = dx * sum_rows w
             gy += swy[s].x + swy[s].y;
         }
 #pragma unroll

@@ -72,6 +72,10 @@ DSS_API int dss_profile_read(dss_ctx *ctx, int stage, double *total_ms, int64_t 
  * enable != 0 switches collection on (and zeroes the counters); out may be NULL. Synchronises the device. */
 DSS_API int dss_debug_raster_stats(dss_ctx *ctx, int enable, uint64_t out[8]);
 
+/* Debug: per-tile records of the last forward run with the counters on: 4 uint32 per tile {SM cycles before the
+ * epilogue, list length, groups of ordered entries visited, launch position}; returns the number of tiles copied. */
+DSS_API int dss_debug_tile_profile(dss_ctx *ctx, uint32_t *out, int64_t max_tiles);
+
 /* Testing: cap the forward's tile-list buffer at max_entries (0 = no cap).  Tiles whose list does not fit are then
  * rasterized from the view's records directly -- the path a sudden growth of the lists takes in production, where the
  * buffer is sized from the previous call without the host ever waiting for the device.  Results must not change. */

@@ -72,11 +72,15 @@ def _run_case(dev, P0, N, S, K, seed, with_coarse_fine):
         # the reference keeps the K nearest by z alone (first come wins a tie), ours by (z, id): pixels where two
         # candidates have exactly the same depth may order them differently -- nothing else may differ
         frac = same.float().mean().item()
-        assert frac > 0.99995, "idx differs on %.5f%% of the pixels" % (100 * (1 - frac))
+        assert frac > 0.999, "idx differs on %.5f%% of the pixels" % (100 * (1 - frac))
         if frac < 1.0:
+            # measured: ~30 of 2.1M pixels at C2 (K = 5), ~120 of 0.5M at K = 8 -- every one an exact tie (scripts/diag_parity.py)
             bad = ~same
             zs, zr = out.zbuf[bad].sort(-1)[0], r_z[bad].sort(-1)[0]
             assert torch.equal(zs, zr), "pixels that differ must hold the same depths (an exact z tie)"
+            tie = (zs[:, 1:] == zs[:, :-1]) & (zs[:, 1:] >= 0)
+            moved = (out.idx[bad].sort(-1)[0] != r_idx[bad].sort(-1)[0]).any(-1)     # tie across the K-th slot
+            assert (tie.any(-1) | moved).all()
         assert torch.equal(r_z[same], out.zbuf[same])
         assert torch.equal(r_q[same], out.qvalue[same])       # same compiler, same expression tree: bit-exact q
         assert torch.equal(r_occ, occ)
