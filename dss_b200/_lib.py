@@ -56,7 +56,6 @@ _SIGNATURES = {
     "dss_profile_read": (C.c_int, [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "dss_debug_raster_stats": (C.c_int, [vp, C.c_int, C.POINTER(C.c_uint64)]),
     "dss_debug_limit_tile_capacity": (C.c_int, [vp, C.c_int64]),
-    "dss_debug_tile_profile": (C.c_int, [vp, vp, C.c_int64]),
     "dss_exclusive_scan_i32": (C.c_int, [vp, vp, vp, C.c_int64, vp]),
     "dss_grid_insert_points_2d": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
     "dss_grid_counting_sort_2d": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
@@ -161,18 +160,9 @@ def raster_stats(enable, device=None):
     """debug counters of the sliced rasterizer accumulated since they were last enabled (see the header)."""
     out = (C.c_uint64 * 8)()
     check(load().dss_debug_raster_stats(ctx(device), int(bool(enable)), out), "dss_debug_raster_stats")
-    names = ["entries_scanned", "survivors", "pixel_tests", "accepted", "entries_sorted", "groups_visited",
+    names = ["entries_scanned", "survivors", "pixel_tests", "accepted", "slices_skipped", "slices_visited",
              "overflow_tiles"]
     return dict(zip(names, [int(v) for v in out[:7]]))
-
-
-def tile_profile(max_tiles=1 << 20, device=None):
-    """(n,4) int64 tensor of per-tile debug records of the last forward run with raster_stats on (see the header)."""
-    buf = torch.zeros((max_tiles, 4), dtype=torch.int32)
-    n = load().dss_debug_tile_profile(ctx(device), vp(buf.data_ptr()), max_tiles)
-    if n < 0:
-        check(n, "dss_debug_tile_profile")
-    return buf[:n].to(torch.int64) & 0xffffffff
 
 
 def limit_tile_capacity(max_entries, device=None):

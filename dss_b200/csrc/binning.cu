@@ -232,20 +232,12 @@ bin_count_kernel(const float4 *__restrict__ rec, const int64_t *__restrict__ fir
     }
 }
 
-// cursors: copy of offsets (N*B*B), advanced atomically; payload: CSR lists of ids (KEYS = false, 4 bytes per entry)
-// or of (z bits, id) keys (KEYS = true, 8 bytes per entry: the rasterizer orders a tile's list by depth without
-// touching the splat records).
-template <bool KEYS>
-__device__ __forceinline__ void put_entry(void *__restrict__ out, int slot, int32_t p, float z) {
-    if (KEYS) reinterpret_cast<uint2 *>(out)[slot] = make_uint2(__float_as_uint(z + 0.0f), (unsigned int)p);
-    else reinterpret_cast<int32_t *>(out)[slot] = p;
-}
-
-template <bool SMEM, bool POW2, bool KEYS>
+// cursors: copy of offsets (N*B*B), advanced atomically; ids: CSR payload.
+template <bool SMEM, bool POW2>
 __global__ void __launch_bounds__(BIN_THREADS)
 bin_scatter_kernel(const float4 *__restrict__ rec, const int64_t *__restrict__ first_idx,
                    const int64_t *__restrict__ num_points, int64_t P0_shared, int S, int bin, int B, int NS,
-                   const float *__restrict__ zrange, int32_t *__restrict__ cursors, void *__restrict__ ids,
+                   const float *__restrict__ zrange, int32_t *__restrict__ cursors, int32_t *__restrict__ ids,
                    int ids_capacity) {
     extern __shared__ int32_t s_hist[];
     const int n = blockIdx.y;
@@ -260,7 +252,6 @@ bin_scatter_kernel(const float4 *__restrict__ rec, const int64_t *__restrict__ f
         __syncthreads();
     }
     unsigned int rect[SMEM ? BIN_ITEMS : 1];
-    float zs[(SMEM && KEYS) ? BIN_ITEMS : 1];
 #pragma unroll
     for (int j = 0; j < BIN_ITEMS; ++j) {
         if (SMEM) rect[j] = BIN_PACK_EMPTY;
@@ -273,7 +264,6 @@ bin_scatter_kernel(const float4 *__restrict__ rec, const int64_t *__restrict__ f
             if (!r.empty) {
                 const int sl = depth_slice(sm, A.z);
                 if (SMEM) rect[j] = pack_rect(r, sl);
-                if (SMEM && KEYS) zs[j] = A.z;
                 for (int by = r.y0; by <= r.y1; ++by)
                     for (int bx = r.x0; bx <= r.x1; ++bx) {
                         const int key = (by * B + bx) * NS + sl;
@@ -281,7 +271,7 @@ bin_scatter_kernel(const float4 *__restrict__ rec, const int64_t *__restrict__ f
                             atomicAdd(&s_hist[key], 1);
                         } else {
                             const int slot = atomicAdd(&cur[key], 1);
-                            if (slot < ids_capacity) put_entry<KEYS>(ids, slot, (int32_t)p, A.z);
+                            if (slot < ids_capacity) ids[slot] = (int32_t)p;
                         }
                     }
             }
@@ -304,7 +294,7 @@ bin_scatter_kernel(const float4 *__restrict__ rec, const int64_t *__restrict__ f
         for (int by = y0; by <= y1; ++by)
             for (int bx = x0; bx <= x1; ++bx) {
                 const int slot = atomicAdd(&s_hist[(by * B + bx) * NS + sl], 1);
-                if (slot < ids_capacity) put_entry<KEYS>(ids, slot, p, (SMEM && KEYS) ? zs[j] : 0.0f);
+                if (slot < ids_capacity) ids[slot] = p;
             }
     }
 }
@@ -365,7 +355,7 @@ int bin_count_and_scan(dss_ctx *ctx, const float4 *rec, const int64_t *first_idx
 
 int bin_scatter(dss_ctx *ctx, const float4 *rec, const int64_t *first_idx, const int64_t *num_points, int N,
                 int64_t P0, int S, int bin, int NS, const float *zrange, const int32_t *offsets, int32_t *cursors,
-                void *ids, int64_t ids_capacity, bool keys, cudaStream_t st) {
+                int32_t *ids, int64_t ids_capacity, cudaStream_t st) {
     const int B = 1 + (S - 1) / bin;
     const int64_t nb = (int64_t)N * B * B * NS;
     const int cap = (int)(ids_capacity > (int64_t)INT32_MAX ? (int64_t)INT32_MAX : ids_capacity);
@@ -373,24 +363,20 @@ int bin_scatter(dss_ctx *ctx, const float4 *rec, const int64_t *first_idx, const
     if (P0 > 0) {
         dim3 grid((unsigned)((P0 + BIN_CHUNK - 1) / BIN_CHUNK), N);
         const bool pow2 = (S & (S - 1)) == 0;
-        const bool smem_ok = (int64_t)B * B * NS <= BIN_MAX_SMEM_TILES && B <= BIN_PACK_MAX_B && NS <= 16 && !ctx->bin_direct;
-        const size_t smem = smem_ok ? (size_t)B * B * NS * sizeof(int32_t) : 0;
         StageScope prof(ctx, ST_BIN_SCATTER, st);
-        auto launch = [&](auto kern) -> int {
-            int rc = prepare_smem(kern, smem);
+        if ((int64_t)B * B * NS <= BIN_MAX_SMEM_TILES && B <= BIN_PACK_MAX_B && NS <= 16 && !ctx->bin_direct) {
+            const size_t smem = (size_t)B * B * NS * sizeof(int32_t);
+            int rc = pow2 ? prepare_smem(bin_scatter_kernel<true, true>, smem) : prepare_smem(bin_scatter_kernel<true, false>, smem);
             if (rc) return rc;
-            kern<<<grid, BIN_THREADS, smem, st>>>(rec, first_idx, num_points, P0, S, bin, B, NS, zrange, cursors, ids, cap);
-            return DSS_OK;
-        };
-        int rc;
-        if (smem_ok) {
-            if (keys) rc = pow2 ? launch(bin_scatter_kernel<true, true, true>) : launch(bin_scatter_kernel<true, false, true>);
-            else rc = pow2 ? launch(bin_scatter_kernel<true, true, false>) : launch(bin_scatter_kernel<true, false, false>);
+            if (pow2)
+                bin_scatter_kernel<true, true><<<grid, BIN_THREADS, smem, st>>>(rec, first_idx, num_points, P0, S, bin, B, NS, zrange, cursors, ids, cap);
+            else
+                bin_scatter_kernel<true, false><<<grid, BIN_THREADS, smem, st>>>(rec, first_idx, num_points, P0, S, bin, B, NS, zrange, cursors, ids, cap);
+        } else if (pow2) {
+            bin_scatter_kernel<false, true><<<grid, BIN_THREADS, 0, st>>>(rec, first_idx, num_points, P0, S, bin, B, NS, zrange, cursors, ids, cap);
         } else {
-            if (keys) rc = pow2 ? launch(bin_scatter_kernel<false, true, true>) : launch(bin_scatter_kernel<false, false, true>);
-            else rc = pow2 ? launch(bin_scatter_kernel<false, true, false>) : launch(bin_scatter_kernel<false, false, false>);
+            bin_scatter_kernel<false, false><<<grid, BIN_THREADS, 0, st>>>(rec, first_idx, num_points, P0, S, bin, B, NS, zrange, cursors, ids, cap);
         }
-        if (rc) return rc;
         DSS_LAUNCH_CHECK(ctx);
     }
     return DSS_OK;
@@ -498,7 +484,7 @@ int dss_rasterize_coarse(dss_ctx *ctx, const float *points, const float *radii, 
     }
     if (total == 0) return DSS_OK;
     return bin_scatter(ctx, rec, first_idx, num_points, N, P, S, bin_size, 1, nullptr, bin_offsets, counts, bin_ids,
-                       bin_ids_capacity, false, st);
+                       bin_ids_capacity, st);
 }
 
 }  // extern "C"

@@ -95,7 +95,6 @@ struct dss_ctx {
     int n_pending, cap_pending;
     int open[8], n_open;
     int raster_stats;   // debug: accumulate raster work counters
-    int64_t raster_dbg_tiles;   // tiles covered by the per-tile debug records of the last forward
     int raster_minb5;   // tuning (env DSS_RASTER_MINB=5): 5 resident CTAs/SM (48 registers) instead of 4 (64)
     int sync_forward;   // tuning (env DSS_SYNC_FORWARD=1): always wait for the tile-list size before the scatter
     cudaEvent_t ev_total;   // (unused since the forward stopped waiting for the tile-list size)
@@ -105,8 +104,6 @@ struct dss_ctx {
     cudaEvent_t ev_fork, ev_join;
     const void *occ_counts_ptr;   // BUF_OCC_COUNTS block known to be all zero (nullptr: unknown)
     size_t occ_counts_elems;
-    int raster_immediate;   // tuning (env DSS_RASTER_IMM=1): insert accepted fragments at once instead of buffering them per warp
-    int raster_flush_min;   // tuning (env DSS_RASTER_FLUSH): see RasterArgs::flush_min, 0 = default
     int ns_override;    // tuning (env DSS_NS): number of depth slices of the forward tile lists, 0 = automatic
     int no_tile_order;  // tuning (env DSS_NO_TILE_ORDER=1): launch the raster tiles in index order
     int occ_tilebin;    // tuning (env DSS_OCC_TILEBIN=1): bin the backward's visible splats by tile only (unordered lists)

@@ -291,10 +291,6 @@ int dss_create(dss_ctx **out) {
         c->occ_tilebin = (tb && tb[0] == '1') ? 1 : 0;
         const char *ns = getenv("DSS_NS");
         c->ns_override = ns ? atoi(ns) : 0;
-        const char *fm = getenv("DSS_RASTER_FLUSH");
-        c->raster_flush_min = fm ? atoi(fm) : 0;
-        const char *im = getenv("DSS_RASTER_IMM");
-        c->raster_immediate = (im && im[0] == '1') ? 1 : 0;
     }
     if (cudaHostAlloc((void **)&c->h_pinned, 64 * sizeof(int64_t), cudaHostAllocMapped) != cudaSuccess) {
         cudaGetLastError();

@@ -26,10 +26,9 @@ int bin_count_and_scan(dss_ctx *ctx, const float4 *rec, const int64_t *first_idx
                        int N, int64_t P0, int S, int bin, int NS, const float *zrange, int32_t *counts,
                        int32_t *offsets, cudaStream_t st);
 
-// ids: int32 id lists (keys = false) or uint2 {z bits, id} lists (keys = true), `ids_capacity` entries either way
 int bin_scatter(dss_ctx *ctx, const float4 *rec, const int64_t *first_idx, const int64_t *num_points, int N,
                 int64_t P0, int S, int bin, int NS, const float *zrange, const int32_t *offsets, int32_t *cursors,
-                void *ids, int64_t ids_capacity, bool keys, cudaStream_t st);
+                int32_t *ids, int64_t ids_capacity, cudaStream_t st);
 
 // Depth slicing shared by the binning and raster kernels (identical arithmetic on both sides).
 struct SliceMap {
@@ -43,7 +42,7 @@ __device__ __forceinline__ SliceMap make_slice_map(const float *zrange, int n, i
     m.zmin = 0.f;
     m.dz = 0.f;
     m.inv_dz = 0.f;
-    if (zrange) {
+    if (NS > 1 && zrange) {
         const float z0 = zrange[2 * n], z1 = zrange[2 * n + 1];
         if (z1 > z0) {
             m.zmin = z0;
@@ -68,16 +67,15 @@ struct RasterArgs {
     const float *cutoff;      // per point (P,) or nullptr -> cutoff_uniform
     float cutoff_uniform;
     const int32_t *tile_offsets;  // (N*B*B + 1)
-    const uint2 *tile_keys;       // CSR payload: {z bits, packed splat id} per entry
+    const int32_t *tile_ids;      // CSR payload: packed splat ids
     const int32_t *tile_order;    // launch order of the tiles (longest lists first) or nullptr: block b = tile b
-    int ids_capacity;             // entries tile_keys can hold; a tile whose list does not fit is rasterized from the
+    int ids_capacity;             // entries tile_ids can hold; a tile whose list does not fit is rasterized from the
                                   // view's records directly (see bin_and_raster)
     const int64_t *first_idx;     // packed layout of the views (nullptr: shared cloud, view n = [n*P0, (n+1)*P0))
     const int64_t *num_points;
     int64_t P0;
     int N, S, K, B;
     int NS;                       // depth slices per tile list
-    int flush_min;                // survivors that trigger a rasterization phase while an ordered list is walked
     const float *zrange;          // (N,2) depth range per view (NS > 1)
     float depth_merge;
     // outputs
@@ -94,7 +92,6 @@ struct RasterArgs {
     uint8_t *visible;      // (P,) must be zeroed by the caller
     int64_t visible_count; // P (to re-zero `visible` when a pass has to be repeated)
     int force_pixel_parallel;  // testing: use the pixel-parallel kernel even for K <= 8
-    uint4 *tile_dbg;           // optional per-tile debug records (with stats)
     unsigned long long *stats; // optional debug counters (dss_debug_raster_stats) or nullptr
 };
 

@@ -67,14 +67,10 @@ DSS_API int dss_profile_read(dss_ctx *ctx, int stage, double *total_ms, int64_t 
 
 /* Debug work counters of the depth-sliced rasterizer (off by default; adds global atomics when on):
  * out[0] tile-list entries scanned, [1] survivors of the block-threshold cull, [2] (splat,pixel) tests,
- * [3] accepted fragments queued for insertion, [4] entries ordered by the in-tile depth sort, [5] groups of 256 ordered
- * entries visited before early termination, [6] tiles rasterized from the records because their list did not fit.
+ * [3] accepted fragments queued for insertion, [4] slices skipped by early termination, [5] rasterization passes
+ * (queue flushes) executed, [6] tiles rasterized from the records because their list did not fit the id buffer.
  * enable != 0 switches collection on (and zeroes the counters); out may be NULL. Synchronises the device. */
 DSS_API int dss_debug_raster_stats(dss_ctx *ctx, int enable, uint64_t out[8]);
-
-/* Debug: per-tile records of the last forward run with the counters on: 4 uint32 per tile {SM cycles before the
- * epilogue, list length, groups of ordered entries visited, launch position}; returns the number of tiles copied. */
-DSS_API int dss_debug_tile_profile(dss_ctx *ctx, uint32_t *out, int64_t max_tiles);
 
 /* Testing: cap the forward's tile-list buffer at max_entries (0 = no cap).  Tiles whose list does not fit are then
  * rasterized from the view's records directly -- the path a sudden growth of the lists takes in production, where the
