@@ -271,11 +271,17 @@ def run_ours(a):
     prm = SplatParams(image_size=S, points_per_pixel=K, cutoff_threshold=1.0, depth_merging_threshold=0.05,
                       antialiasing_sigma=1.0, radii_backward_scaler=5.0, clip_pts_grad=0.05,
                       backface_culling=False, znear=0.1, zfar=100.0)            # configs/dss.yml:14-22
+    from dss_b200.parallel import GradSync, assign_views, view_costs_from_cameras
     pts, nrm, col = sphere_cloud(P0, seed=0)
     cams = random_cameras(V * world, seed=0)
     proj_all, view_all = camera_matrices(cams)
-    sl = slice(rank * V, (rank + 1) * V)                       # this rank's contiguous slice of the views
-    proj_h, view_h = proj_all[sl].contiguous().pin_memory(), view_all[sl].contiguous().pin_memory()
+    # views are dealt to the ranks by estimated cost (close cameras cover more pixels): the slowest rank sets the step
+    mine = assign_views(view_costs_from_cameras(view_all).tolist(), world)[rank]
+    assert len(mine) == V
+    proj_h, view_h = proj_all[mine].contiguous().pin_memory(), view_all[mine].contiguous().pin_memory()
+    # the one exchange step of the path: per-point gradients summed over the ranks, issued by
+    # the backward itself and overlapped with it (dss_b200/parallel.py)
+    sync = GradSync(timing=True) if world > 1 else None
     g = torch.Generator().manual_seed(99 + rank)
     # colours: one RGB per POINT, shared by the views of the step (the quantity an inverse-rendering step optimises
     # and the one exchange step reduces); per-(view,point) colours -- the layout the reference holds on the device after
@@ -293,15 +299,9 @@ def run_ours(a):
     def step_resident():
         pts_d.grad = None
         col_d.grad = None
-        out = render_points(pts_d, nrm_d, col_d, proj_d, view_d, h_d, prm)
-        out.image.backward(grad_d)
+        out = render_points(pts_d, nrm_d, col_d, proj_d, view_d, h_d, prm, grad_sync=sync)
+        out.image.backward(grad_d)            # gradients come back already summed over the ranks
         return out
-
-    def allreduce_grads():
-        # the one exchange step of the path: sum of point gradients over all views
-        buf = torch.cat([pts_d.grad, col_d.grad], 1)      # (P0, 6): d position, d colour
-        dist.all_reduce(buf)
-        return buf
 
     def sync_all():
         torch.cuda.synchronize()
@@ -311,10 +311,12 @@ def run_ours(a):
 
     # ---- device-timed region: inputs resident in HBM ----
     for _ in range(max(a.warmup, 3)):
-        step_resident()
-        if world > 1:
-            allreduce_grads()
+        last = step_resident()
     sync_all()
+    n_visible = int(last.visible.sum().item())     # visible (view, point) pairs of this rank's step (for the byte counts)
+    if sync is not None:
+        sync.timings_ms()
+        sync.reset_counters()
     _lib.profile_reset(dev)
     _lib.profile_enable(True, dev)
     launches0 = _lib.launch_count(dev)
@@ -324,11 +326,18 @@ def run_ours(a):
     e0.record()
     for _ in range(a.steps):
         step_resident()
-        if world > 1:
-            allreduce_grads()
     e1.record()
     sync_all()
     clocks = sampler.stop()
+    allreduce = None
+    if sync is not None:
+        ar_ms = sync.timings_ms() / a.steps
+        ar_bytes = sync.bytes_reduced / a.steps
+        allreduce = {"ms_per_step": ar_ms, "bytes_per_step": int(ar_bytes), "collectives_per_step": 2,
+                     "busbw_GBs": (2.0 * (world - 1) / world) * ar_bytes / (ar_ms * 1e-3) / 1e9 if ar_ms > 0 else None,
+                     "overlap": "d colour reduced on a side stream during the occupancy gather; d position behind the "
+                                "chain kernel"}
+        sync.timing = False
     ms = e0.elapsed_time(e1)
     launches = _lib.launch_count(dev) - launches0
     stages = _lib.profile_read(dev)
@@ -394,16 +403,10 @@ def run_ours(a):
             mark("compute_begin", main)
             p = d[0].detach().requires_grad_(True)
             c = d[2].detach().requires_grad_(True)
-            out = render_points(p, d[1], c, d[3], d[4], d[5], prm)
+            out = render_points(p, d[1], c, d[3], d[4], d[5], prm, grad_sync=sync)
             mark("forward_end", main)
             out.image.backward(d[6])
-            gp, gc = p.grad, c.grad
-            if world > 1:
-                # the one exchange step of the path: sum of the point gradients over all ranks' views; the reduced
-                # gradients are what goes back to the host
-                sync = torch.cat([gp, gc], 1)
-                dist.all_reduce(sync)
-                gp, gc = sync[:, :3], sync[:, 3:]
+            gp, gc = p.grad, c.grad        # summed over all ranks' views: the reduced gradients go back to the host
             ev_done[slot].record(main)
             mark("compute_end", main)
             with torch.cuda.stream(back_stream):
@@ -458,34 +461,49 @@ def run_ours(a):
     dom = max(stages, key=lambda k: stages[k][0])
     dom_ms, dom_n = stages[dom]
     per_launch_views = V
-    alg = {
-        # algorithmic bytes per launch (one launch covers the V views of a step); DESIGN.md "Roofline"
+    Pv = n_visible                 # visible (view, point) pairs of one step, measured (about 18 % of V*P0)
+    alg_all = {
+        # algorithmic bytes per step of every stage (its kernels cover the V views of a step); DESIGN.md section 5
+        "preprocess": per_launch_views * (24 * P0 + 36 * P0),            # read pos+normal, write record + scaler
+        "bin_count": per_launch_views * 20 * P0,                          # read 20 B of every record
+        "bin_scatter": per_launch_views * 24 * P0,                        # + 4 B id per entry written (>= 1 per splat)
         "raster_forward": per_launch_views * (36 * P0 + (16 + 4 * K) * S * S),
-        # planes (read alpha 16 B/px of the image gradient, write 2 planes) + gather (read both planes once, read the
-        # compact records of the visible splats, write their gradients): upper bound with P_vis = P0
-        "occ_backward": per_launch_views * ((16 + 8) * S * S + 8 * S * S + 28 * P0),
-        "occ_bin": per_launch_views * 9 * P0,
-        "preprocess": per_launch_views * (24 * P0 + 36 * P0),
-        "bin_count": per_launch_views * 20 * P0, "bin_scatter": per_launch_views * 24 * P0,
-        "colour_backward": per_launch_views * ((16 + 8 * K) * S * S + 12 * P0),
-        "chain_world": per_launch_views * 20 * P0 + 24 * P0,
-        "search_radius": per_launch_views * 4 * 9 * P0,
-    }.get(dom, 0)
+        # backward binning: visibility byte + record head of every splat, compact record + id of the visible ones
+        "occ_bin": 2 * (per_launch_views * P0 * 1 + Pv * 16) + Pv * 20,
+        "search_radius": 4 * Pv * 16,                                     # four radix passes over the compact records
+        # planes (read the alpha gradient, write g-/g+ once) + gather (read both planes once, compact records, ids,
+        # write the gradients of the VISIBLE splats)
+        "occ_backward": per_launch_views * ((4 + 8) * S * S + 8 * S * S) + Pv * 28,
+        "colour_backward": per_launch_views * ((16 + 8 * K) * S * S) + 12 * P0,
+        "chain_world": per_launch_views * 8 * P0 + 24 * P0,
+    }
+    traffic_all = {}
+    try:    # measured DRAM bytes per launch (dram__bytes_read + write, one ncu --set full capture per kernel change)
+        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        if P0 == 1_000_000 and S == 512 and V == 8 and K == 5:
+            traffic_all = {k: v for k, v in tr.items() if isinstance(v, (int, float))}
+    except Exception:
+        pass
+    per_kernel = {}
+    for k, (ms_tot, n_br) in stages.items():
+        if not n_br or k not in alg_all:
+            continue
+        ms_k = ms_tot / max(a.steps, 1)
+        gbs = alg_all[k] / (ms_k * 1e-3) / 1e9 if ms_k > 0 else 0.0
+        per_kernel[k] = {"ms": ms_k, "algorithmic_bytes": int(alg_all[k]), "achieved": gbs, "frac": gbs / peak,
+                         "traffic": traffic_all.get(k)}
+    alg = alg_all.get(dom, 0)
     dom_avg_ms = dom_ms / max(a.steps, 1)      # per step: a stage's kernels are launched once per step
     achieved = alg / (dom_avg_ms * 1e-3) / 1e9 if dom_avg_ms > 0 else 0.0
     step_bytes = V * algorithmic_bytes_per_view(P0, S, K)
     step_gbs = step_bytes / (ms_max / a.steps * 1e-3) / 1e9
-    traffic = None
-    try:    # measured DRAM bytes per launch of this stage's kernel, from the committed ncu --set full capture
-        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-        if P0 == 1_000_000 and S == 512 and V == 8 and K == 5:
-            traffic = tr.get(dom)
-    except Exception:
-        pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic_all.get(dom), "peak_source": peak_src,
                 "kernel_ms_per_launch": dom_avg_ms, "kernel_share_of_step": dom_ms / total_stage_ms,
                 "stage_ms_per_step": {k: v[0] / a.steps for k, v in stages.items() if v[1]},
+                # every stage against its own byte roofline (both dominant kernels are always in here: which of the two
+                # is `kernel` can flip from run to run)
+                "kernels": per_kernel, "visible_pairs_per_step": int(Pv),
                 "whole_step": {"algorithmic_bytes": step_bytes, "achieved": step_gbs, "frac": step_gbs / peak,
                                "formula": BYTES_PER_SPLAT_FMT}}
 
@@ -503,12 +521,14 @@ def run_ours(a):
         "warmup": max(a.warmup, 3), "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "synthetic sphere %d pts x %d views/GPU, %dx%d, K=%d, fwd+bwd" % (P0, V, S, S, K),
-                   "views_total": V * world, "parallelism": "views sharded %d/GPU + 1 NCCL allreduce of point grads" % V
+                   "views_total": V * world, "parallelism": "views dealt by cost, %d/GPU; NCCL all-reduce of d colour (side stream, "
+                   "overlapped with the occupancy gather) and of d position (behind the chain kernel)" % V
                    if world > 1 else "single GPU",
                    "l2": "per-step inputs %.0f MB + %.0f MB of splat records exceed the 126 MB L2" % (work_mb, V * P0 * 32 / 1e6),
                    "colours": "per point (P0,3), shared by the views",
                    "settings": "configs/dss.yml:14-22 (cutoff 1, merge 0.05, K=5, radii_s 5, clip 0.05, sigma 1)"},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "allreduce": allreduce,
     }
     print(json.dumps(line))
     if world > 1:

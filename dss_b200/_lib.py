@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libdss_b200.so")
 DSS_OK = 0
 DSS_E_CAPACITY = -4
 MAX_POINTS_PER_PIXEL = 64
+MAX_SHARED_VIEWS = 256
 
 _lib = None
 _ctx = {}
@@ -73,6 +74,7 @@ _SIGNATURES = {
     "dss_preprocess": (C.c_int, [vp, C.POINTER(RenderArgs), vp]),
     "dss_render_forward": (C.c_int, [vp, C.POINTER(RenderArgs), vp]),
     "dss_render_backward": (C.c_int, [vp, C.POINTER(RenderArgs), vp]),
+    "dss_colour_backward": (C.c_int, [vp, C.POINTER(RenderArgs), vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

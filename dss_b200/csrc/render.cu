@@ -154,6 +154,42 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const __grid_constant__
     }
 }
 
+// Fork/join of the context's side stream: once work has been forked, EVERY return path makes the caller's stream wait
+// for it (an error return that skipped the join would let the caller free tensors the side stream still writes).
+struct SideJoin {
+    dss_ctx *ctx;
+    cudaStream_t st;
+    bool forked = false, joined = false;
+    SideJoin(dss_ctx *c, cudaStream_t s) : ctx(c), st(s) {}
+    int fork() {
+        DSS_CUDA_TRY(cudaEventRecord(ctx->ev_fork, st));
+        DSS_CUDA_TRY(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+        forked = true;
+        return DSS_OK;
+    }
+    int join() {
+        if (!forked || joined) return DSS_OK;
+        joined = true;
+        DSS_CUDA_TRY(cudaEventRecord(ctx->ev_join, ctx->side));
+        DSS_CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+        return DSS_OK;
+    }
+    ~SideJoin() {
+        if (forked && !joined) {
+            cudaEventRecord(ctx->ev_join, ctx->side);
+            cudaStreamWaitEvent(st, ctx->ev_join, 0);
+        }
+    }
+};
+
+static int run_colour_backward(dss_ctx *ctx, const dss_render_args *g, cudaStream_t on) {
+    const int N = g->n_views, S = g->image_size, K = g->points_per_pixel;
+    const int64_t npix = (int64_t)N * S * S;
+    const int64_t cP0 = (g->shared_cloud && g->shared_colours) ? g->P0 : 0;
+    DSS_CUDA_TRY(cudaMemsetAsync(g->grad_colours, 0, (size_t)(cP0 > 0 ? cP0 : g->P) * 3 * sizeof(float), on));
+    return colour_backward(ctx, g->idx, g->weights, g->grad_image, npix, K, g->grad_colours, cP0, (int64_t)S * S, on);
+}
+
 static int check_common(const dss_render_args *g) {
     DSS_REQUIRE(g != nullptr, "args is null");
     DSS_REQUIRE(g->n_views > 0, "n_views must be positive");
@@ -164,6 +200,7 @@ static int check_common(const dss_render_args *g) {
                 "points_per_pixel must be in [1, 64]");
     DSS_REQUIRE(g->shared_cloud || (g->first_idx && g->num_points), "first_idx/num_points required");
     DSS_REQUIRE(!g->shared_cloud || g->P == (int64_t)g->n_views * g->P0, "P != n_views * P0");
+    DSS_REQUIRE(!g->shared_cloud || g->n_views <= DSS_MAX_SHARED_VIEWS, "a shared cloud takes at most 256 views per call");
     return DSS_OK;
 }
 
@@ -366,6 +403,16 @@ int dss_render_forward(dss_ctx *ctx, const dss_render_args *g, void *stream) {
     return bin_and_raster(ctx, a, g->shared_cloud ? nullptr : g->first_idx, g->num_points, g->P0, st);
 }
 
+int dss_colour_backward(dss_ctx *ctx, const dss_render_args *g, void *stream) {
+    using namespace dss;
+    DSS_REQUIRE(ctx != nullptr, "ctx is null");
+    int rc = check_common(g);
+    if (rc) return rc;
+    DSS_REQUIRE(g->grad_image && g->idx && g->weights && g->grad_colours, "colour backward needs grad_image, idx, weights, grad_colours");
+    if (g->P == 0) return DSS_OK;
+    return run_colour_backward(ctx, g, (cudaStream_t)stream);
+}
+
 int dss_render_backward(dss_ctx *ctx, const dss_render_args *g, void *stream) {
     using namespace dss;
     cudaStream_t st = (cudaStream_t)stream;
@@ -389,24 +436,18 @@ int dss_render_backward(dss_ctx *ctx, const dss_render_args *g, void *stream) {
     if ((rc = ctx_get(ctx, BUF_RS, (size_t)N, &rs))) return rc;
     if ((rc = ctx_get(ctx, BUF_GRADXY, (size_t)(2 * P), &gxy))) return rc;
     // The colour scatter does not depend on the occupancy path: fork it onto the context's side stream so that its
-    // atomics overlap the (latency-bound) binning / median kernels, join before returning to the caller's stream.
-    const bool fork_colours = g->grad_colours != nullptr;
-    if (fork_colours) {
-        DSS_CUDA_TRY(cudaEventRecord(ctx->ev_fork, st));
-        DSS_CUDA_TRY(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
-        const int64_t cP0 = (g->shared_cloud && g->shared_colours) ? g->P0 : 0;
-        DSS_CUDA_TRY(cudaMemsetAsync(g->grad_colours, 0, (size_t)(cP0 > 0 ? cP0 : P) * 3 * sizeof(float), ctx->side));
-        if ((rc = colour_backward(ctx, g->idx, g->weights, g->grad_image, npix, K, g->grad_colours, cP0, (int64_t)S * S,
-                                  ctx->side)))
-            return rc;
-        DSS_CUDA_TRY(cudaEventRecord(ctx->ev_join, ctx->side));
+    // atomics overlap the (latency-bound) binning / median kernels, join before the chain kernel (and on every return).
+    SideJoin side(ctx, st);
+    if (g->grad_colours != nullptr) {
+        if ((rc = side.fork())) return rc;
+        if ((rc = run_colour_backward(ctx, g, ctx->side))) return rc;
     }
     if ((rc = occ_backward(ctx, rec, g->visible, rs, g->radii_backward_scaler, g->grad_image, 4, 3, fi, g->num_points, N,
                            g->P0, S, gxy, st)))
         return rc;
     if (g->search_radius)
         DSS_CUDA_TRY(cudaMemcpyAsync(g->search_radius, rs, (size_t)N * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    if (fork_colours) DSS_CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+    if ((rc = side.join())) return rc;
     float *gz = nullptr;
     if (g->grad_zbuf) {
         if ((rc = ctx_get(ctx, BUF_MISC, (size_t)P, &gz))) return rc;
@@ -429,7 +470,6 @@ int dss_render_backward(dss_ctx *ctx, const dss_render_args *g, void *stream) {
     c.grad_world = g->grad_points_world;
     StageScope prof(ctx, ST_CHAIN, st);
     if (g->shared_cloud) {
-        DSS_REQUIRE(N <= 256, "shared-cloud backward supports at most 256 views per call");
         chain_kernel<<<nblocks(g->P0, 256, ctx->sm_count, 8), 256, (size_t)N * 32 * sizeof(float), st>>>(c);
     } else {
         dim3 grid(nblocks(g->P0, 256, ctx->sm_count, 8), N);

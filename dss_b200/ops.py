@@ -72,17 +72,27 @@ def _fill_common(a, points, normals, colours, proj, view, h, first_idx, num_poin
 def _layout(points, proj, first_idx, num_points, shared):
     N = proj.shape[0]
     if shared:
+        if N > _lib.MAX_SHARED_VIEWS:   # the backward's chain kernel holds the view matrices in shared memory
+            raise RuntimeError("a shared cloud takes at most %d views per call, got %d" % (_lib.MAX_SHARED_VIEWS, N))
         P0 = points.shape[0]
         return N, P0, N * P0
     if first_idx is None or num_points is None:
         raise RuntimeError("packed clouds need cloud_to_packed_first_idx and num_points_per_cloud")
     P = points.shape[0]
+    # the kernels read both arrays as int64[N] and index the packed arrays with them: check before any launch
+    # (their VALUES stay on the device -- reading them back would put a host sync into every forward; rows that no
+    #  range covers get zero gradients, see backward)
+    for name, t in (("cloud_to_packed_first_idx", first_idx), ("num_points_per_cloud", num_points)):
+        if t.dtype != torch.int64 or tuple(t.shape) != (N,):
+            raise RuntimeError("%s must be an int64 tensor of shape (%d,), got %s %s"
+                               % (name, N, t.dtype, tuple(t.shape)))
     return N, P, P   # P0 is only an upper bound on the points of one view in packed mode
 
 
 class _RenderFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, points, normals, colours, proj, view, h, first_idx, num_points, shared, prm, want_frags):
+    def forward(ctx, points, normals, colours, proj, view, h, first_idx, num_points, shared, prm, want_frags,
+                grad_sync=None):
         dev = _lib.require_cuda(points, normals, colours, proj, view, h, first_idx, num_points)
         points_c = _lib.as_f32(points.detach(), "points")
         normals_c = _lib.as_f32(normals.detach(), "normals")
@@ -125,7 +135,7 @@ class _RenderFunction(torch.autograd.Function):
         # fill kernels over ~400 MB per backward); backward() handles None
         ctx.set_materialize_grads(False)
         ctx.save_for_backward(points_c, proj_c, view_c, records, idx, weights, visible, fi, npts)
-        ctx.meta = (shared, prm, N, P0, P, want_frags, shared_col)
+        ctx.meta = (shared, prm, N, P0, P, want_frags, shared_col, grad_sync)
         outs = (image, idx, weights, visible, records, scaler)
         if want_frags:
             ctx.mark_non_differentiable(idx, weights, visible, records, scaler, qvalue)
@@ -136,7 +146,7 @@ class _RenderFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_image, *rest):
         points_c, proj_c, view_c, records, idx, weights, visible, fi, npts = ctx.saved_tensors
-        shared, prm, N, P0, P, want_frags, shared_col = ctx.meta
+        shared, prm, N, P0, P, want_frags, shared_col, grad_sync = ctx.meta
         dev = points_c.device
         grad_zbuf = rest[5] if (want_frags and len(rest) > 5) else None
         if grad_image is None:
@@ -145,21 +155,38 @@ class _RenderFunction(torch.autograd.Function):
         if grad_zbuf is not None:
             grad_zbuf = _lib.as_f32(grad_zbuf, "grad_zbuf")
         grad_colours = torch.empty((P0 if shared_col else P, 3), dtype=torch.float32, device=dev)
-        grad_points = torch.empty_like(points_c)
+        # packed clouds: rows no view range covers are never written by the kernels
+        grad_points = torch.empty_like(points_c) if shared else torch.zeros_like(points_c)
         a = _lib.RenderArgs()
         _fill_common(a, points_c, None, None, proj_c, view_c, None, fi, npts, shared, N, P0, P, prm)
         a.records, a.idx, a.weights, a.visible = _lib.ptr(records), _lib.ptr(idx), _lib.ptr(weights), _lib.ptr(visible)
         a.shared_colours = int(shared_col)
         a.grad_image, a.grad_zbuf = _lib.ptr(grad_image), _lib.ptr(grad_zbuf)
         a.grad_colours, a.grad_points_world = _lib.ptr(grad_colours), _lib.ptr(grad_points)
+        lib = _lib.load()
         with torch.cuda.device(dev):
-            rc = _lib.load().dss_render_backward(_lib.ctx(dev), C.byref(a), _lib.stream_ptr(dev))
-        _lib.check(rc, "dss_render_backward")
-        return (grad_points, None, grad_colours) + (None,) * 8
+            if grad_sync is None:
+                rc = lib.dss_render_backward(_lib.ctx(dev), C.byref(a), _lib.stream_ptr(dev))
+                _lib.check(rc, "dss_render_backward")
+            else:
+                # data-parallel step (dss_b200/parallel.py): the colour gradients are final after the colour scatter --
+                # reduce them over the ranks on a side stream while the occupancy path runs here
+                main, side = torch.cuda.current_stream(dev), grad_sync.side_stream(dev)
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    rc = lib.dss_colour_backward(_lib.ctx(dev), C.byref(a), _lib.stream_ptr(dev))
+                    _lib.check(rc, "dss_colour_backward")
+                    grad_sync.reduce_early(grad_colours)
+                a.grad_colours = _lib.ptr(None)
+                rc = lib.dss_render_backward(_lib.ctx(dev), C.byref(a), _lib.stream_ptr(dev))
+                _lib.check(rc, "dss_render_backward")
+                grad_sync.reduce_late(grad_points)
+                grad_sync.join(dev)
+        return (grad_points, None, grad_colours) + (None,) * 9
 
 
 def render_points(points, normals, colours, proj, view, h, params: SplatParams, first_idx=None, num_points=None,
-                  shared_cloud=True, return_fragments=False) -> RenderOutput:
+                  shared_cloud=True, return_fragments=False, grad_sync=None) -> RenderOutput:
     """Render ``N`` views of an oriented point cloud to RGBA.
 
     points, normals : (P0,3) when ``shared_cloud`` (one cloud seen from N cameras) else packed (P,3)
@@ -167,9 +194,11 @@ def render_points(points, normals, colours, proj, view, h, params: SplatParams, 
                       features used by every view of a shared cloud (gradient then summed over the views)
     proj, view      : (N,4,4) full-projection and world-to-view matrices, row-vector convention
     h               : (N,) per-view or (P,) per-splat variance scale (rasterizer.py:293-402)
+    grad_sync       : optional dss_b200.parallel.GradSync -- the backward then returns gradients already summed over the
+                      ranks of a view-sharded step, the collectives overlapped with the backward kernels
     """
     outs = _RenderFunction.apply(points, normals, colours, proj, view, h, first_idx, num_points,
-                                 bool(shared_cloud), params, bool(return_fragments))
+                                 bool(shared_cloud), params, bool(return_fragments), grad_sync)
     image, idx, weights, visible, records, scaler = outs[:6]
     zbuf, qvalue = (outs[6], outs[7]) if return_fragments else (None, None)
     return RenderOutput(image, idx, zbuf, qvalue, weights, visible, records, scaler)

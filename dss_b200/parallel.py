@@ -1,19 +1,26 @@
 """View-sharded data parallelism for the splatting path.
 
-Views are independent units: the N views of a step are split contiguously over the G ranks (one process per
-GPU), every rank holds the full cloud, renders and back-propagates its own slice, and ONE all-reduce(sum) of
-the packed point-gradient buffer (d position | d normal | d colour, (P0, 9) fp32) makes the gradients
-identical everywhere, so identical optimizer steps need no parameter broadcast.  No other collective is on
-the path.  Works with any torch.distributed backend ("nccl" over NVLink on the B200 box, "gloo" in the CPU
-tests); there is no collective inside the kernels because the path has no exchange step other than this one.
+Views are independent units: the views of a step are dealt to the G ranks (one process per GPU), every rank holds the
+full cloud, renders and back-propagates its own views, and the per-point gradients (d position | d normal | d colour)
+are summed over the ranks so that identical optimizer steps need no parameter broadcast.  No other collective is on
+the path, and none is needed inside the kernels.
+
+The exchange is OVERLAPPED with the backward pass instead of trailing it (round 1 issued one all-reduce of a
+``torch.cat`` copy behind the last kernel: 0.36 ms of a 2.27 ms step at 8 GPUs).  The colour-side gradients are final as
+soon as the colour scatter has run, long before the occupancy path finishes, so :class:`GradSync` reduces them on a
+side stream while the occupancy gather (the longest kernel of the backward) is still running; only the position
+gradients, final after the last kernel, are reduced behind it.  No staging copy: both collectives run in place on
+the tensors the backward returns.
+
+Works with any torch.distributed backend ("nccl" over NVLink on the B200 box, "gloo" in the CPU tests).
 """
-from typing import Optional, Sequence, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_views", "pack_point_grads", "unpack_point_grads", "allreduce_point_grads",
-           "allreduce_visibility"]
+__all__ = ["shard_views", "assign_views", "view_costs_from_cameras", "GradSync", "pack_point_grads",
+           "unpack_point_grads", "allreduce_point_grads", "allreduce_visibility"]
 
 
 def shard_views(n_views: int, world_size: int, rank: int) -> Tuple[int, int]:
@@ -25,9 +32,116 @@ def shard_views(n_views: int, world_size: int, rank: int) -> Tuple[int, int]:
     return start, start + base + (1 if rank < extra else 0)
 
 
+def assign_views(costs: Sequence[float], world_size: int) -> List[List[int]]:
+    """Deal views to ranks so that every rank gets the same NUMBER of views (+-1) and about the same COST.
+
+    Views differ up to 3x in cost (a close camera covers more pixels and has a wider backward window) and the slowest
+    rank sets the step time.  Views are sorted by decreasing cost and dealt in snake order (0..G-1, G-1..0, ...): equal
+    counts by construction, and the cost sums differ by at most one view's cost.  ``costs`` can be any estimate -- the
+    previous step's per-view visible-point count times its search radius squared, or :func:`view_costs_from_cameras`.
+    Returns ``world_size`` lists of view indices (each sorted ascending)."""
+    if world_size <= 0:
+        raise ValueError("bad world_size")
+    order = sorted(range(len(costs)), key=lambda i: (-float(costs[i]), i))
+    out: List[List[int]] = [[] for _ in range(world_size)]
+    for k, v in enumerate(order):
+        r = k % world_size
+        if (k // world_size) % 2 == 1:
+            r = world_size - 1 - r
+        out[r].append(v)
+    return [sorted(x) for x in out]
+
+
+def view_costs_from_cameras(view_matrices: torch.Tensor) -> torch.Tensor:
+    """Cheap cost estimate from the world-to-view matrices (N,4,4; row-vector convention): the projected area of the
+    object, hence the number of covered tiles and the area of the backward window, falls with the squared camera
+    distance."""
+    t = view_matrices[:, 3, :3].double()
+    return 1.0 / (t * t).sum(-1).clamp_min(1e-12)
+
+
+class GradSync:
+    """Sums the per-point gradients over the ranks, overlapped with the backward pass.
+
+    Pass an instance as ``grad_sync=`` to :func:`dss_b200.ops.render_points`.  The backward then
+      1. runs the colour scatter on this object's side stream and calls :meth:`reduce_early` on the colour-side
+         gradients there (the collective starts while the occupancy path runs on the main stream),
+      2. runs the occupancy path and the chain kernel on the main stream and calls :meth:`reduce_late` on the position
+         gradients,
+      3. makes the main stream wait for the side stream (:meth:`join`).
+    With world size 1 (or torch.distributed not initialised) every method is a no-op apart from the stream handling, so
+    the same training step runs on one GPU.  ``timing=True`` records CUDA events around both collectives; read them
+    with :meth:`timings_ms` (synchronises)."""
+
+    def __init__(self, group=None, timing: bool = False):
+        self.group = group
+        self.timing = timing
+        self._side = {}
+        self._events = []
+        self.bytes_reduced = 0
+        self.calls = 0
+
+    # -- plumbing --------------------------------------------------------------------------------
+    @property
+    def world_size(self) -> int:
+        if not (dist.is_available() and dist.is_initialized()):
+            return 1
+        return dist.get_world_size(self.group)
+
+    def side_stream(self, device) -> "torch.cuda.Stream":
+        key = torch.device(device).index
+        if key not in self._side:
+            self._side[key] = torch.cuda.Stream(device=device)
+        return self._side[key]
+
+    def _reduce(self, tensors: Sequence[Optional[torch.Tensor]]):
+        tensors = [t for t in tensors if t is not None]
+        if not tensors or self.world_size == 1:
+            return
+        ev = None
+        if self.timing and tensors[0].is_cuda:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
+        for t in tensors:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            self.bytes_reduced += t.numel() * t.element_size()
+        if ev is not None:
+            ev[1].record()
+            self._events.append(ev)
+
+    # -- called by the backward ------------------------------------------------------------------
+    def reduce_early(self, *tensors):
+        """colour-side gradients (d colour, d normal): issued on the CURRENT stream, which is the side stream."""
+        self._reduce(tensors)
+
+    def reduce_late(self, *tensors):
+        """position gradients: issued on the current (main) stream behind the chain kernel."""
+        self._reduce(tensors)
+        self.calls += 1
+
+    def join(self, device):
+        torch.cuda.current_stream(device).wait_stream(self.side_stream(device))
+
+    # -- reporting -------------------------------------------------------------------------------
+    def timings_ms(self) -> float:
+        """Total device time of the recorded collectives (both streams; they overlap with compute)."""
+        total = 0.0
+        for a, b in self._events:
+            b.synchronize()
+            total += a.elapsed_time(b)
+        self._events = []
+        return total
+
+    def reset_counters(self):
+        self._events = []
+        self.bytes_reduced = 0
+        self.calls = 0
+
+
 def pack_point_grads(grad_points: Optional[torch.Tensor], grad_normals: Optional[torch.Tensor],
                      grad_colours: Optional[torch.Tensor], P0: int, device=None) -> torch.Tensor:
-    """(P0, 9) fp32 buffer [d pos | d normal | d colour]; missing parts are zero."""
+    """(P0, 9) fp32 buffer [d pos | d normal | d colour]; missing parts are zero.  (For callers that want ONE collective
+    behind the backward; :class:`GradSync` needs no packing.)"""
     ref = next(t for t in (grad_points, grad_normals, grad_colours) if t is not None)
     buf = torch.zeros((P0, 9), dtype=torch.float32, device=device if device is not None else ref.device)
     for i, t in enumerate((grad_points, grad_normals, grad_colours)):

@@ -42,6 +42,7 @@ extern "C" {
 #define DSS_E_CAPACITY -4   /* caller-provided output capacity too small (see *_required)     */
 
 #define DSS_MAX_POINTS_PER_PIXEL 64   /* reference allows 150 (rasterization_utils.cuh:18); configs use 5 / 8 */
+#define DSS_MAX_SHARED_VIEWS 256      /* views of one shared cloud per render call (checked by forward AND backward) */
 
 typedef struct dss_ctx dss_ctx;   /* owns grow-only device scratch for one device; not thread-safe */
 
@@ -235,11 +236,17 @@ typedef struct dss_render_args {
     int32_t reserved0;
 } dss_render_args;
 
-/* preprocess -> bin -> rasterize + blend.  Waits once for the event that marks the tile-list size (the kernels
- * behind it are already queued from the second call on; see DESIGN.md "Host side"). */
+/* preprocess -> bin -> rasterize + blend.  Never waits for the device in steady state: the tile-list buffer is sized
+ * from the total the PREVIOUS call published; tiles whose list has outgrown it are rasterized from the records on the
+ * device (see DESIGN.md "Host side").  Only a context's first call synchronises once to size the buffer. */
 DSS_API int dss_render_forward(dss_ctx *ctx, const dss_render_args *args, void *stream);
-/* visibility/median radius -> occupancy gather -> colour scatter -> z scatter -> clip -> world chain. */
+/* visibility/median radius -> occupancy gather -> colour scatter -> z scatter -> clip -> world chain.
+ * grad_colours == NULL skips the colour scatter (see dss_colour_backward). */
 DSS_API int dss_render_backward(dss_ctx *ctx, const dss_render_args *args, void *stream);
+/* The colour half of the backward alone (norm_weighted_sum backward: grad_colours[idx_k] += g_rgb * w_k), on `stream`.
+ * Lets a data-parallel caller start the all-reduce of the colour gradients while dss_render_backward (called with
+ * grad_colours == NULL on another stream) is still busy with the occupancy path (dss_b200/parallel.py). */
+DSS_API int dss_colour_backward(dss_ctx *ctx, const dss_render_args *args, void *stream);
 /* per-(point,view) preprocess only (rasterizer.py:443-565 fused): writes ndc, ellipse, radii, scaler. */
 DSS_API int dss_preprocess(dss_ctx *ctx, const dss_render_args *args, void *stream);
 

@@ -172,3 +172,35 @@ def test_shared_point_colours_equal_repeated_colours(cuda_device):
     assert torch.equal(p1.grad, p2.grad)
     assert tuple(c2.grad.shape) == (P0, 3)
     torch.testing.assert_close(c2.grad, c1.grad.view(N, P0, 3).sum(0), rtol=1e-4, atol=1e-9)
+
+
+def test_grad_sync_path_equals_plain_backward(cuda_device):
+    """render_points(grad_sync=GradSync()) splits the backward into dss_colour_backward (side stream) and
+    dss_render_backward without the colour half (dss_b200/parallel.py); on one rank the collectives are no-ops and the
+    gradients must be those of the single-call backward: positions bit for bit, colours up to atomic order."""
+    from dss_b200.parallel import GradSync
+    P0, N, S = 15000, 3, 96
+    pts, nrm, col, proj, view, cams = scene(P0, N, seed=17)
+    d = cuda_device
+    prm = SplatParams(image_size=S, znear=0.1, clip_pts_grad=0.05)
+    h = torch.full((N,), 3e-4).to(d)
+    g = (torch.randn(N, S, S, 4, generator=torch.Generator().manual_seed(6)) * 1e-3).to(d)
+    res = []
+    for sync in (None, GradSync(timing=True)):
+        p = pts.to(d).requires_grad_(True)
+        c = col.to(d).requires_grad_(True)
+        o = render_points(p, nrm.to(d), c, proj.to(d), view.to(d), h, prm, grad_sync=sync)
+        o.image.backward(g)
+        torch.cuda.synchronize()
+        res.append((p.grad.clone(), c.grad.clone()))
+    assert torch.equal(res[0][0], res[1][0])
+    torch.testing.assert_close(res[0][1], res[1][1], rtol=1e-4, atol=1e-10)
+
+
+def test_more_than_256_shared_views_is_refused_before_any_launch(cuda_device):
+    d = cuda_device
+    pts, nrm, col, proj, view, cams = scene(100, 1, seed=1)
+    N = 257
+    with pytest.raises(RuntimeError, match="at most 256 views"):
+        render_points(pts.to(d), nrm.to(d), col.to(d), proj.repeat(N, 1, 1).to(d), view.repeat(N, 1, 1).to(d),
+                      torch.full((N,), 3e-4, device=d), SplatParams(image_size=32, znear=0.1))

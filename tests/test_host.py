@@ -181,7 +181,8 @@ def test_shard_views_partitions_contiguously():
 _WORKER = r'''
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, %(root)r)
-from dss_b200.parallel import shard_views, pack_point_grads, allreduce_point_grads, allreduce_visibility
+from dss_b200.parallel import (shard_views, pack_point_grads, allreduce_point_grads, allreduce_visibility, GradSync,
+                               assign_views)
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%(port)d", rank=int(sys.argv[1]), world_size=2)
 rank, P0, V = dist.get_rank(), 50, 5
 g = torch.Generator().manual_seed(7)
@@ -195,9 +196,40 @@ vis = torch.zeros(P0, dtype=torch.bool); vis[rank::7] = True
 both = allreduce_visibility(vis)
 exp = torch.zeros(P0, dtype=torch.bool); exp[0::7] = True; exp[1::7] = True
 assert torch.equal(both, exp)
+# the overlapped exchange of a view-sharded step: views dealt by cost, colour-side gradients reduced early, position
+# gradients late -- every rank ends up with the sum over ALL views
+costs = [5.0, 1.0, 3.0, 2.0, 4.0]
+mine = assign_views(costs, 2)[rank]
+sync = GradSync()
+assert sync.world_size == 2
+gc, gp = per_view[mine].sum(0) * 2, per_view[mine].sum(0)
+sync.reduce_early(gc, None)
+sync.reduce_late(gp)
+assert torch.allclose(gp, per_view.sum(0), atol=1e-5) and torch.allclose(gc, 2 * per_view.sum(0), atol=1e-5)
+assert sync.calls == 1 and sync.bytes_reduced == 2 * P0 * 3 * 4
 dist.destroy_process_group()
 print("rank", rank, "ok")
 '''
+
+
+def test_assign_views_balances_count_and_cost():
+    from dss_b200.parallel import assign_views, view_costs_from_cameras
+    costs = [9.0, 1.0, 1.0, 8.0, 2.0, 7.0, 3.0, 6.0, 4.0, 5.0, 5.0, 4.0, 6.0, 3.0, 7.0, 2.0]
+    for world in (1, 2, 4, 8):
+        parts = assign_views(costs, world)
+        assert sorted(v for p in parts for v in p) == list(range(len(costs)))
+        assert {len(p) for p in parts} == {len(costs) // world}
+        sums = [sum(costs[v] for v in p) for p in parts]
+        assert max(sums) - min(sums) <= max(costs)
+        # contiguous slices of the same views are worse (or equal) for the slowest rank
+        per = len(costs) // world
+        contiguous = max(sum(costs[r * per:(r + 1) * per]) for r in range(world))
+        assert max(sums) <= contiguous + 1e-9
+    assert assign_views([1.0, 2.0, 3.0], 2) == [[2], [0, 1]]            # uneven count: 3 | 1 + 2
+    view = torch.eye(4).repeat(3, 1, 1)
+    view[:, 3, :3] = torch.tensor([[0.0, 0.0, 1.0], [0.0, 0.0, 2.0], [0.0, 2.0, 2.0]])
+    c = view_costs_from_cameras(view)
+    assert c[0] > c[1] > c[2]
 
 
 def test_view_sharded_allreduce_two_gloo_processes():
