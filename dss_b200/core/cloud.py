@@ -186,3 +186,37 @@ class PointCloudsFilters:
         sel = lambda lst: None if lst is None else [t[mask[i, : t.shape[0]]] for i, t in enumerate(lst)]
         return PointClouds3D(sel(point_clouds.points_list()), sel(point_clouds.normals_list()),
                              sel(point_clouds.features_list()))
+
+
+# ---- duck typing for foreign cloud containers --------------------------------------------------------------------
+# The reference hands pytorch3d ``Pointclouds`` (or its own ``PointClouds3D`` subclass) to the renderer; the filter's
+# ``filter_with`` returns exactly that type (DSS/core/cloud.py).  Those objects have ``points_list`` / ``normals_list`` /
+# ``equisized`` but neither ``shares_points`` nor ``equal_sized``, and their ``extend()`` CLONES the tensors, so storage
+# aliasing never identifies a shared cloud there: fall back to shapes and, for clouds of equal shape, to the contents.
+def clouds_equal_sized(point_clouds) -> bool:
+    f = getattr(point_clouds, "equal_sized", None)
+    if callable(f):
+        return bool(f())
+    eq = getattr(point_clouds, "equisized", None)
+    if eq is not None:
+        return bool(eq() if callable(eq) else eq)
+    return len({int(p.shape[0]) for p in point_clouds.points_list()}) <= 1
+
+
+def clouds_share_points(point_clouds) -> bool:
+    f = getattr(point_clouds, "shares_points", None)
+    if callable(f):
+        return bool(f())
+    pts = point_clouds.points_list()
+    if len(pts) <= 1:
+        return True
+    if any(p.shape != pts[0].shape for p in pts):
+        return False
+    nl = getattr(point_clouds, "normals_list", None)
+    nrm = nl() if callable(nl) else None
+
+    def same(group):
+        g0 = group[0]
+        return all(t.data_ptr() == g0.data_ptr() or torch.equal(t, g0) for t in group[1:])
+
+    return same(pts) and (nrm is None or same(nrm))

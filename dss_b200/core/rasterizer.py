@@ -19,6 +19,7 @@ import torch.nn as nn
 from .. import _C
 from ..ops import SplatParams, preprocess_points
 from .camera import camera_matrices
+from .cloud import clouds_share_points
 from .knn import knn_sq_dists
 
 __all__ = ["PointFragments", "PointsRasterizationSettings", "SurfaceSplatting", "rasterize_elliptical_points",
@@ -134,7 +135,7 @@ class SurfaceSplatting(nn.Module):
                 and self._Vrk_h.shape[0] == int(num.sum())):
             return self._Vrk_h
         pts_list = point_clouds.points_list()
-        shared = point_clouds.shares_points()
+        shared = clouds_share_points(point_clouds)
         per_cloud = []
         for n, pts in enumerate(pts_list):
             if shared and n > 0:

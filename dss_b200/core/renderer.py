@@ -13,6 +13,7 @@ import torch.nn as nn
 
 from ..ops import render_points
 from .camera import camera_matrices
+from .cloud import clouds_equal_sized, clouds_share_points
 from .rasterizer import PointFragments, _splat_params
 
 __all__ = ["SurfaceSplattingRenderer", "NormWeightedCompositor"]
@@ -66,7 +67,7 @@ class SurfaceSplattingRenderer(nn.Module):
                 h = rast._compute_h(point_clouds, **kwargs)
         feats = point_clouds.features_packed()[:, :3].contiguous()
         verbose = kwargs.get("verbose", False)
-        if point_clouds.shares_points() and point_clouds.equal_sized():
+        if clouds_share_points(point_clouds) and clouds_equal_sized(point_clouds):
             out = render_points(point_clouds.points_list()[0], point_clouds.normals_list()[0], feats, proj.to(dev),
                                 view.to(dev), h.to(dev), prm, shared_cloud=True, return_fragments=verbose)
         else:

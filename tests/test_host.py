@@ -246,3 +246,37 @@ def test_view_sharded_allreduce_two_gloo_processes():
         outs = [p.communicate(timeout=180)[0] for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and "rank %d ok" % r in o, o
+
+
+class _ForeignClouds:
+    """Only the accessor set of pytorch3d.structures.Pointclouds that the path touches (no shares_points/equal_sized);
+    like pytorch3d's extend(), every cloud holds its own CLONE of the data."""
+
+    def __init__(self, pts, nrm, n):
+        self._p = [pts.clone() for _ in range(n)]
+        self._n = [nrm.clone() for _ in range(n)]
+        self.equisized = True
+
+    def points_list(self):
+        return self._p
+
+    def normals_list(self):
+        return self._n
+
+    def __len__(self):
+        return len(self._p)
+
+
+def test_foreign_cloud_containers_are_duck_typed():
+    from dss_b200.core.cloud import PointClouds3D, clouds_equal_sized, clouds_share_points
+    g = torch.Generator().manual_seed(0)
+    pts, nrm = torch.randn(50, 3, generator=g), torch.randn(50, 3, generator=g)
+    foreign = _ForeignClouds(pts, nrm, 3)
+    assert clouds_equal_sized(foreign) and clouds_share_points(foreign)          # cloned, same content: shared
+    foreign._p[2] = foreign._p[2] + 1e-3
+    assert not clouds_share_points(foreign)
+    foreign._p[2] = torch.randn(40, 3, generator=g)
+    foreign.equisized = False
+    assert not clouds_share_points(foreign) and not clouds_equal_sized(foreign)
+    ours = PointClouds3D([pts], normals=[nrm]).extend(3)
+    assert clouds_share_points(ours) and clouds_equal_sized(ours)
