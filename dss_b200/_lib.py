@@ -16,6 +16,7 @@ DSS_OK = 0
 DSS_E_CAPACITY = -4
 MAX_POINTS_PER_PIXEL = 64
 MAX_SHARED_VIEWS = 256
+MAX_LIGHTS = 8
 
 _lib = None
 _ctx = {}
@@ -39,7 +40,11 @@ class RenderArgs(C.Structure):
         ("idx", vp), ("weights", vp), ("zbuf", vp), ("qvalue", vp), ("visible", vp),
         ("grad_image", vp), ("grad_zbuf", vp), ("grad_colours", vp), ("grad_ndc", vp),
         ("grad_points_world", vp), ("search_radius", vp),
-        ("shared_colours", C.c_int32), ("reserved0", C.c_int32),
+        ("shared_colours", C.c_int32),
+        ("shade", C.c_int32), ("n_lights", C.c_int32), ("light_type", C.c_int32), ("shininess", C.c_float),
+        ("reserved0", C.c_int32),
+        ("albedo", vp), ("lights", vp), ("ambient", vp), ("cam_centres", vp), ("shaded", vp),
+        ("grad_albedo", vp), ("grad_normals_world", vp), ("grad_points_shading", vp),
     ]
 
 

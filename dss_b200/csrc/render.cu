@@ -15,6 +15,12 @@ static inline unsigned int nblocks(int64_t items, int threads, int sm_count, int
     return (unsigned int)b;
 }
 
+struct ShadeArgs {
+    const float *albedo, *lights, *ambient, *cam;
+    int n_lights, light_type;
+    float shininess;
+};
+
 struct PreArgs {
     const float *pts, *nrm, *proj, *view, *h;
     const int64_t *first_idx, *num_points;
@@ -24,6 +30,8 @@ struct PreArgs {
     float4 *rec;
     float *ndc, *ellipse, *radii, *scaler;
     int32_t *zrange;   // (N,2) float bits: min / max view depth of the renderable splats, or null
+    ShadeArgs sh;      // sh.albedo != nullptr: write the shaded colour of every (view, point) to `shaded`
+    float *shaded;
 };
 
 // Fast reciprocal / division / square root (MUFU based, <= 2 ulp): the per-splat quantities are compared with the
@@ -44,6 +52,83 @@ __device__ __forceinline__ float py_eps_denom(float d) { return eps_denom(d, 1e-
 __device__ __forceinline__ float py_eps_sqrt(float s) { return fmaxf(fabsf(s), 1e-17f); }
 
 // ---------------------------------------------------------------------------------------------
+// Per-point shading: DSS/core/texture.py:74-127 (LightingTexture.forward:
+// shaded = rgb * (ambient + diffuse) + specular) over DSS/core/lighting.py:10-172 (diffuse: Lambert with the
+// renormalised normal and light direction, :62-69; specular: reflected ray against the view direction, masked where
+// the light is behind the surface, :139-172).  Lights sit in shared memory as rows of 9 floats.
+// ---------------------------------------------------------------------------------------------
+struct V3 {
+    float x, y, z;
+};
+__device__ __forceinline__ V3 v3(float x, float y, float z) { return V3{x, y, z}; }
+__device__ __forceinline__ float dot3(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ V3 add3(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ V3 sub3(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ V3 mul3(V3 a, float s) { return v3(a.x * s, a.y * s, a.z * s); }
+// F.normalize(x, p=2, dim=-1, eps=1e-6): x / max(|x|, eps); returns the (clamped) norm through `len`
+__device__ __forceinline__ V3 normalize3(V3 a, float &len) {
+    len = fmaxf(sqrtf(dot3(a, a)), 1e-6f);
+    return mul3(a, 1.0f / len);
+}
+// gradient of y = normalize(x) given dL/dy (for |x| > eps; below it the map is linear: g / eps)
+__device__ __forceinline__ V3 normalize3_bwd(V3 y, float len, V3 gy) {
+    if (len <= 1e-6f) return mul3(gy, 1.0f / len);
+    return mul3(sub3(gy, mul3(y, dot3(y, gy))), 1.0f / len);
+}
+
+// forward (and, with gc != nullptr, backward) of the shading of one (view, point).  sL: lights in shared memory.
+//   colour = albedo * (ambient + diffuse) + specular
+// backward: accumulates d albedo, d normal (un-normalised input normal), d position into g_alb / g_nrm / g_pos.
+template <bool BACKWARD>
+__device__ __forceinline__ V3 shade_point(const float *sL, int n_lights, int light_type, float shininess, V3 amb, V3 p,
+                                          V3 nrm, V3 alb, V3 cam, V3 gc, V3 &g_alb, V3 &g_nrm, V3 &g_pos) {
+    float nlen, vlen;
+    const V3 nh = normalize3(nrm, nlen);
+    const V3 v = normalize3(sub3(cam, p), vlen);
+    V3 diff = v3(0.f, 0.f, 0.f), spec = v3(0.f, 0.f, 0.f);
+    V3 g_nh = v3(0.f, 0.f, 0.f), g_v = v3(0.f, 0.f, 0.f);
+    for (int l = 0; l < n_lights; ++l) {
+        const float *L = sL + l * 9;
+        float dlen;
+        const V3 draw = light_type ? sub3(v3(L[0], L[1], L[2]), p) : v3(L[0], L[1], L[2]);
+        const V3 d = normalize3(draw, dlen);
+        const V3 cd = v3(L[3], L[4], L[5]), cs = v3(L[6], L[7], L[8]);
+        const float cosang = dot3(nh, d);
+        const float lam = fmaxf(cosang, 0.0f);                           // lighting.py:65
+        diff = add3(diff, mul3(cd, lam));
+        const float mask = cosang > 0.0f ? 1.0f : 0.0f;                   // :158
+        const V3 r = add3(mul3(d, -1.0f), mul3(nh, 2.0f * cosang));       // :163
+        const float vr = dot3(v, r);
+        const float alpha = fmaxf(vr, 0.0f) * mask;                       // :166-167
+        const float pw = alpha > 0.0f ? powf(alpha, shininess) : 0.0f;    // :169
+        spec = add3(spec, mul3(cs, pw));
+        if (BACKWARD) {
+            // diffuse: d/d cos = sum_c (gc*alb)_c cd_c  where cos > 0
+            float g_cos = (cosang > 0.0f) ? (gc.x * alb.x * cd.x + gc.y * alb.y * cd.y + gc.z * alb.z * cd.z) : 0.0f;
+            V3 g_d = v3(0.f, 0.f, 0.f);
+            if (alpha > 0.0f) {
+                const float g_alpha = dot3(gc, cs) * shininess * powf(alpha, shininess - 1.0f);
+                const float g_vr = g_alpha;                                // alpha = vr where vr > 0 and mask = 1
+                const V3 g_r = mul3(v, g_vr);
+                g_v = add3(g_v, mul3(r, g_vr));
+                g_cos += 2.0f * dot3(g_r, nh);
+                g_nh = add3(g_nh, mul3(g_r, 2.0f * cosang));
+                g_d = sub3(g_d, g_r);
+            }
+            g_nh = add3(g_nh, mul3(d, g_cos));
+            g_d = add3(g_d, mul3(nh, g_cos));
+            if (light_type) g_pos = sub3(g_pos, normalize3_bwd(d, dlen, g_d));   // d = normalize(loc - p)
+        }
+    }
+    if (BACKWARD) {
+        g_alb = add3(g_alb, v3(gc.x * (amb.x + diff.x), gc.y * (amb.y + diff.y), gc.z * (amb.z + diff.z)));
+        g_nrm = add3(g_nrm, normalize3_bwd(nh, nlen, g_nh));
+        g_pos = sub3(g_pos, normalize3_bwd(v, vlen, g_v));                // v = normalize(cam - p)
+    }
+    return v3(alb.x * (amb.x + diff.x) + spec.x, alb.y * (amb.y + diff.y) + spec.y, alb.z * (amb.z + diff.z) + spec.z);
+}
+
+// ---------------------------------------------------------------------------------------------
 // One thread per (view, point).  Fuses DSS/core/rasterizer.py:183-217 (depth filter), :148-181
 // (backface filter), :443-496 (_compute_WJk), :293-342 (global/isotropic Vrk with Sk^T Sk = I - n n^T),
 // :404-441 (variance + detMk), :525-565 (conic, radii, scaler) and the pytorch3d transform of :614
@@ -51,12 +136,22 @@ __device__ __forceinline__ float py_eps_sqrt(float s) { return fmaxf(fabsf(s), 1
 // Filtered points keep their slot but get z = -1, which every later stage treats as "not renderable"
 // exactly like the reference treats points behind the camera (rasterize_points.cu:87-88).
 // ---------------------------------------------------------------------------------------------
+template <bool SHADE>
 __global__ void __launch_bounds__(256) preprocess_kernel(const __grid_constant__ PreArgs a) {
     __shared__ float sM[16], sV[16];
+    __shared__ float sL[DSS_MAX_LIGHTS * 9 + 6];   // lights, ambient (3), camera centre (3)
     const int n = blockIdx.y;
     if (threadIdx.x < 16) {
         sM[threadIdx.x] = a.proj[n * 16 + threadIdx.x];
         sV[threadIdx.x] = a.view[n * 16 + threadIdx.x];
+    }
+    constexpr bool shade = SHADE;
+    if (shade) {
+        if (threadIdx.x < a.sh.n_lights * 9) sL[threadIdx.x] = a.sh.lights[threadIdx.x];
+        if (threadIdx.x < 3) {
+            sL[DSS_MAX_LIGHTS * 9 + threadIdx.x] = a.sh.ambient[threadIdx.x];
+            sL[DSS_MAX_LIGHTS * 9 + 3 + threadIdx.x] = a.sh.cam[n * 3 + threadIdx.x];
+        }
     }
     __syncthreads();
     const ViewRange vr = view_range(a.shared_cloud ? nullptr : a.first_idx, a.num_points, n, a.P0);
@@ -133,6 +228,17 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const __grid_constant__
             a.radii[s * 2 + 0] = rx;
             a.radii[s * 2 + 1] = ry;
         }
+        if (shade) {
+            V3 ga, gn, gp;
+            const float *amb = sL + DSS_MAX_LIGHTS * 9;
+            const V3 c = shade_point<false>(sL, a.sh.n_lights, a.sh.light_type, a.sh.shininess, v3(amb[0], amb[1], amb[2]),
+                                            v3(p0, p1, p2), v3(n0, n1, n2),
+                                            v3(a.sh.albedo[src * 3], a.sh.albedo[src * 3 + 1], a.sh.albedo[src * 3 + 2]),
+                                            v3(amb[3], amb[4], amb[5]), v3(0.f, 0.f, 0.f), ga, gn, gp);
+            a.shaded[s * 3 + 0] = c.x;
+            a.shaded[s * 3 + 1] = c.y;
+            a.shaded[s * 3 + 2] = c.z;
+        }
     }
     if (a.zrange) {   // one pair of atomics per block
         __shared__ int s_lo[8], s_hi[8];
@@ -151,6 +257,44 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const __grid_constant__
             atomicMin(&a.zrange[2 * n], zlo);
             atomicMax(&a.zrange[2 * n + 1], zhi);
         }
+    }
+}
+
+// d L / d shaded (N*P0,3) -> d albedo, d normal, d position (through the shading) per world point, summed over the views:
+// one thread per point loops over the views (deterministic, no atomics) and re-evaluates the lighting of the
+// (view, point) pairs that received a colour gradient (the visible ones, ~18 %).
+struct ShadeBwdArgs {
+    const float *pts, *nrm, *gsh;
+    ShadeArgs sh;
+    int64_t P0;
+    int N;
+    float *g_alb, *g_nrm, *g_pos;
+};
+
+__global__ void __launch_bounds__(256) shade_backward_kernel(const __grid_constant__ ShadeBwdArgs a) {
+    extern __shared__ float sS[];   // lights (L*9), ambient (3), camera centres (N*3)
+    const int nl9 = a.sh.n_lights * 9;
+    for (int i = threadIdx.x; i < nl9; i += blockDim.x) sS[i] = a.sh.lights[i];
+    for (int i = threadIdx.x; i < 3; i += blockDim.x) sS[nl9 + i] = a.sh.ambient[i];
+    for (int i = threadIdx.x; i < a.N * 3; i += blockDim.x) sS[nl9 + 3 + i] = a.sh.cam[i];
+    __syncthreads();
+    const V3 amb = v3(sS[nl9], sS[nl9 + 1], sS[nl9 + 2]);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.P0; i += (int64_t)gridDim.x * blockDim.x) {
+        const V3 p = v3(a.pts[i * 3], a.pts[i * 3 + 1], a.pts[i * 3 + 2]);
+        const V3 nrm = v3(a.nrm[i * 3], a.nrm[i * 3 + 1], a.nrm[i * 3 + 2]);
+        const V3 alb = v3(a.sh.albedo[i * 3], a.sh.albedo[i * 3 + 1], a.sh.albedo[i * 3 + 2]);
+        V3 ga = v3(0.f, 0.f, 0.f), gn = v3(0.f, 0.f, 0.f), gp = v3(0.f, 0.f, 0.f);
+        for (int n = 0; n < a.N; ++n) {
+            const float *g = a.gsh + ((int64_t)n * a.P0 + i) * 3;
+            const V3 gc = v3(g[0], g[1], g[2]);
+            if (gc.x == 0.0f && gc.y == 0.0f && gc.z == 0.0f) continue;
+            const float *c = sS + nl9 + 3 + n * 3;
+            shade_point<true>(sS, a.sh.n_lights, a.sh.light_type, a.sh.shininess, amb, p, nrm, alb, v3(c[0], c[1], c[2]), gc,
+                              ga, gn, gp);
+        }
+        a.g_alb[i * 3] = ga.x, a.g_alb[i * 3 + 1] = ga.y, a.g_alb[i * 3 + 2] = ga.z;
+        a.g_nrm[i * 3] = gn.x, a.g_nrm[i * 3 + 1] = gn.y, a.g_nrm[i * 3 + 2] = gn.z;
+        a.g_pos[i * 3] = gp.x, a.g_pos[i * 3 + 1] = gp.y, a.g_pos[i * 3 + 2] = gp.z;
     }
 }
 
@@ -185,9 +329,34 @@ struct SideJoin {
 static int run_colour_backward(dss_ctx *ctx, const dss_render_args *g, cudaStream_t on) {
     const int N = g->n_views, S = g->image_size, K = g->points_per_pixel;
     const int64_t npix = (int64_t)N * S * S;
-    const int64_t cP0 = (g->shared_cloud && g->shared_colours) ? g->P0 : 0;
+    const int64_t cP0 = (g->shared_cloud && g->shared_colours && !g->shade) ? g->P0 : 0;
     DSS_CUDA_TRY(cudaMemsetAsync(g->grad_colours, 0, (size_t)(cP0 > 0 ? cP0 : g->P) * 3 * sizeof(float), on));
-    return colour_backward(ctx, g->idx, g->weights, g->grad_image, npix, K, g->grad_colours, cP0, (int64_t)S * S, on);
+    int rc = colour_backward(ctx, g->idx, g->weights, g->grad_image, npix, K, g->grad_colours, cP0, (int64_t)S * S, on);
+    if (rc || !g->shade) return rc;
+    // shading backward: d shaded (N*P0,3) -> d albedo, d normal, d position, per world point
+    DSS_REQUIRE(g->grad_albedo && g->grad_normals_world && g->grad_points_shading && g->points_world,
+                "shading backward needs grad_albedo, grad_normals_world, grad_points_shading");
+    ShadeBwdArgs b;
+    b.pts = g->points_world;
+    b.nrm = g->normals_world;
+    b.gsh = g->grad_colours;
+    b.sh.albedo = g->albedo;
+    b.sh.lights = g->lights;
+    b.sh.ambient = g->ambient;
+    b.sh.cam = g->cam_centres;
+    b.sh.n_lights = g->n_lights;
+    b.sh.light_type = g->light_type;
+    b.sh.shininess = g->shininess;
+    b.P0 = g->P0;
+    b.N = N;
+    b.g_alb = g->grad_albedo;
+    b.g_nrm = g->grad_normals_world;
+    b.g_pos = g->grad_points_shading;
+    StageScope prof(ctx, ST_COLOUR_BWD, on);
+    const size_t smem = (size_t)(g->n_lights * 9 + 3 + N * 3) * sizeof(float);
+    shade_backward_kernel<<<nblocks(g->P0, 256, ctx->sm_count, 8), 256, smem, on>>>(b);
+    DSS_LAUNCH_CHECK(ctx);
+    return DSS_OK;
 }
 
 static int check_common(const dss_render_args *g) {
@@ -201,6 +370,12 @@ static int check_common(const dss_render_args *g) {
     DSS_REQUIRE(g->shared_cloud || (g->first_idx && g->num_points), "first_idx/num_points required");
     DSS_REQUIRE(!g->shared_cloud || g->P == (int64_t)g->n_views * g->P0, "P != n_views * P0");
     DSS_REQUIRE(!g->shared_cloud || g->n_views <= DSS_MAX_SHARED_VIEWS, "a shared cloud takes at most 256 views per call");
+    if (g->shade) {
+        DSS_REQUIRE(g->shared_cloud, "fused shading needs a shared cloud");
+        DSS_REQUIRE(g->n_lights >= 1 && g->n_lights <= DSS_MAX_LIGHTS, "n_lights must be in [1, 8]");
+        DSS_REQUIRE(g->albedo && g->lights && g->ambient && g->cam_centres && g->normals_world, "shading needs albedo, lights, ambient, cam_centres, normals");
+        DSS_REQUIRE(g->light_type == 0 || g->light_type == 1, "light_type must be 0 (directional) or 1 (point)");
+    }
     return DSS_OK;
 }
 
@@ -234,9 +409,22 @@ static int run_preprocess(dss_ctx *ctx, const dss_render_args *g, float4 *rec, c
     a.radii = g->radii;
     a.scaler = g->scaler;
     a.zrange = reinterpret_cast<int32_t *>(zrange);
+    memset(&a.sh, 0, sizeof(a.sh));
+    a.shaded = nullptr;
+    if (g->shade && g->shaded) {
+        a.sh.albedo = g->albedo;
+        a.sh.lights = g->lights;
+        a.sh.ambient = g->ambient;
+        a.sh.cam = g->cam_centres;
+        a.sh.n_lights = g->n_lights;
+        a.sh.light_type = g->light_type;
+        a.sh.shininess = g->shininess;
+        a.shaded = g->shaded;
+    }
     dim3 grid(nblocks(g->P0, 256, ctx->sm_count, 8), g->n_views);
     StageScope prof(ctx, ST_PREPROCESS, st);
-    preprocess_kernel<<<grid, 256, 0, st>>>(a);
+    if (a.shaded) preprocess_kernel<true><<<grid, 256, 0, st>>>(a);
+    else preprocess_kernel<false><<<grid, 256, 0, st>>>(a);
     DSS_LAUNCH_CHECK(ctx);
     return DSS_OK;
 }
@@ -248,6 +436,7 @@ static int run_preprocess(dss_ctx *ctx, const dss_render_args *g, float4 *rec, c
 // and writes the sum (deterministic, no atomics); otherwise one thread per packed splat.
 // ---------------------------------------------------------------------------------------------
 struct ChainArgs {
+    const float *gshade;   // (P0,3) position gradient through the shading, added to the result (shared cloud), or null
     const float *pts, *proj, *view;
     const float2 *gxy;     // (P,2) occupancy gradient
     const float *gz;       // (P,) z gradient or null
@@ -318,6 +507,11 @@ __global__ void __launch_bounds__(256) chain_kernel(const __grid_constant__ Chai
                     acc2 += w2;
                 }
             }
+            if (a.gshade) {
+                acc0 += a.gshade[i * 3 + 0];
+                acc1 += a.gshade[i * 3 + 1];
+                acc2 += a.gshade[i * 3 + 2];
+            }
             a.grad_world[i * 3 + 0] = acc0;
             a.grad_world[i * 3 + 1] = acc1;
             a.grad_world[i * 3 + 2] = acc2;
@@ -371,7 +565,8 @@ int dss_render_forward(dss_ctx *ctx, const dss_render_args *g, void *stream) {
     DSS_REQUIRE(ctx != nullptr, "ctx is null");
     int rc = check_common(g);
     if (rc) return rc;
-    DSS_REQUIRE(g->image && g->idx && g->scaler && g->colours, "forward needs image, idx, scaler, colours");
+    DSS_REQUIRE(g->image && g->idx && g->scaler && (g->shade ? (const void *)g->shaded : (const void *)g->colours),
+                "forward needs image, idx, scaler and colours (or, with shade, the shaded output)");
     float4 *rec = reinterpret_cast<float4 *>(g->records);
     if (!rec && (rc = ctx_get(ctx, BUF_RECORDS, (size_t)(2 * (g->P > 0 ? g->P : 1)), &rec))) return rc;
     DSS_REQUIRE((reinterpret_cast<uintptr_t>(rec) & 15) == 0, "records must be 16-byte aligned");
@@ -393,8 +588,8 @@ int dss_render_forward(dss_ctx *ctx, const dss_render_args *g, void *stream) {
     a.qvalue = g->qvalue;
     a.occ = nullptr;
     a.scaler = g->scaler;
-    a.colours = g->colours;
-    a.colour_P0 = (g->shared_cloud && g->shared_colours) ? g->P0 : 0;
+    a.colours = g->shade ? g->shaded : g->colours;
+    a.colour_P0 = (g->shared_cloud && g->shared_colours && !g->shade) ? g->P0 : 0;
     a.image = g->image;
     a.weights = g->weights;
     a.visible = g->visible;
@@ -455,6 +650,7 @@ int dss_render_backward(dss_ctx *ctx, const dss_render_args *g, void *stream) {
         if ((rc = zbuf_backward(ctx, g->idx, g->grad_zbuf, npix, K, gz, 1, st))) return rc;
     }
     ChainArgs c;
+    c.gshade = (g->shade && g->grad_colours != nullptr) ? g->grad_points_shading : nullptr;
     c.pts = g->points_world;
     c.proj = g->proj;
     c.view = g->view;

@@ -16,7 +16,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["SplatParams", "RenderOutput", "render_points", "preprocess_points"]
+__all__ = ["SplatParams", "Shading", "make_shading", "RenderOutput", "render_points", "preprocess_points"]
 
 
 class SplatParams(NamedTuple):
@@ -32,6 +32,16 @@ class SplatParams(NamedTuple):
     zfar: float = 100.0
 
 
+class Shading(NamedTuple):
+    """Fused per-point shading: pass as ``shading=`` with the per-point albedo as ``colours``.
+    Build it from the light objects with :func:`make_shading`."""
+    lights: torch.Tensor         # (L,9) {direction | location, diffuse rgb, specular rgb}
+    ambient: torch.Tensor        # (3,)
+    cam_centres: torch.Tensor    # (N,3) camera centres in world space
+    light_type: int = 0          # 0 directional, 1 point
+    shininess: float = 64.0
+
+
 class RenderOutput(NamedTuple):
     image: torch.Tensor      # (N,S,S,4) rgb + occupancy
     idx: torch.Tensor        # (N,S,S,K) int32
@@ -41,6 +51,25 @@ class RenderOutput(NamedTuple):
     visible: torch.Tensor    # (P,) uint8
     records: torch.Tensor    # (P,8) {x,y,z,rx, ry,a,b,c}
     scaler: torch.Tensor     # (P,)
+
+
+def _fill_shading(a, sh, albedo):
+    a.shade = 1
+    a.n_lights = int(sh.lights.shape[0])
+    a.light_type = int(sh.light_type)
+    a.shininess = float(sh.shininess)
+    a.albedo, a.lights, a.ambient, a.cam_centres = _lib.ptr(albedo), _lib.ptr(sh.lights), _lib.ptr(sh.ambient), \
+        _lib.ptr(sh.cam_centres)
+
+
+def _check_shading(sh, N, dev):
+    if sh.lights.dim() != 2 or sh.lights.shape[1] != 9 or not (1 <= sh.lights.shape[0] <= _lib.MAX_LIGHTS):
+        raise RuntimeError("shading.lights must be (L,9) with 1 <= L <= %d" % _lib.MAX_LIGHTS)
+    if tuple(sh.ambient.shape) != (3,) or tuple(sh.cam_centres.shape) != (N, 3):
+        raise RuntimeError("shading.ambient must be (3,) and shading.cam_centres (N,3)")
+    _lib.require_cuda(sh.lights, sh.ambient, sh.cam_centres)
+    return Shading(_lib.as_f32(sh.lights.detach(), "lights"), _lib.as_f32(sh.ambient.detach(), "ambient"),
+                   _lib.as_f32(sh.cam_centres.detach(), "cam_centres"), int(sh.light_type), float(sh.shininess))
 
 
 def _fill_common(a, points, normals, colours, proj, view, h, first_idx, num_points, shared, N, P0, P, prm):
@@ -92,7 +121,7 @@ def _layout(points, proj, first_idx, num_points, shared):
 class _RenderFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, points, normals, colours, proj, view, h, first_idx, num_points, shared, prm, want_frags,
-                grad_sync=None):
+                grad_sync=None, shading=None):
         dev = _lib.require_cuda(points, normals, colours, proj, view, h, first_idx, num_points)
         points_c = _lib.as_f32(points.detach(), "points")
         normals_c = _lib.as_f32(normals.detach(), "normals")
@@ -101,7 +130,11 @@ class _RenderFunction(torch.autograd.Function):
         view_c = _lib.as_f32(view.detach(), "view")
         h_c = _lib.as_f32(h.detach().reshape(-1), "h")
         N, P0, P = _layout(points_c, proj_c, first_idx, num_points, shared)
-        shared_col = bool(shared) and N > 1 and tuple(colours_c.shape) == (P0, 3)
+        if shading is not None:
+            if not shared or tuple(colours_c.shape) != (P0, 3):
+                raise RuntimeError("fused shading takes a shared cloud and the per-point albedo (P0,3) as colours")
+            shading = _check_shading(shading, N, dev)
+        shared_col = bool(shared) and (N > 1 or shading is not None) and tuple(colours_c.shape) == (P0, 3)
         if tuple(colours_c.shape) != (P, 3) and not shared_col:
             raise RuntimeError("colours must have shape (%d, 3)%s, got %s"
                                % (P, " or (%d, 3)" % P0 if shared else "", tuple(colours_c.shape)))
@@ -126,6 +159,11 @@ class _RenderFunction(torch.autograd.Function):
         a = _lib.RenderArgs()
         _fill_common(a, points_c, normals_c, colours_c, proj_c, view_c, h_c, fi, npts, shared, N, P0, P, prm)
         a.shared_colours = int(shared_col)
+        shaded = None
+        if shading is not None:
+            shaded = torch.empty((P, 3), **f32)
+            _fill_shading(a, shading, colours_c)
+            a.shaded = _lib.ptr(shaded)
         a.records, a.scaler, a.image, a.idx = _lib.ptr(records), _lib.ptr(scaler), _lib.ptr(image), _lib.ptr(idx)
         a.weights, a.visible, a.zbuf, a.qvalue = _lib.ptr(weights), _lib.ptr(visible), _lib.ptr(zbuf), _lib.ptr(qvalue)
         with torch.cuda.device(dev):
@@ -135,6 +173,7 @@ class _RenderFunction(torch.autograd.Function):
         # fill kernels over ~400 MB per backward); backward() handles None
         ctx.set_materialize_grads(False)
         ctx.save_for_backward(points_c, proj_c, view_c, records, idx, weights, visible, fi, npts)
+        ctx.shading = (shading, normals_c, colours_c) if shading is not None else None
         ctx.meta = (shared, prm, N, P0, P, want_frags, shared_col, grad_sync)
         outs = (image, idx, weights, visible, records, scaler)
         if want_frags:
@@ -154,7 +193,11 @@ class _RenderFunction(torch.autograd.Function):
         grad_image = _lib.as_f32(grad_image, "grad_image")
         if grad_zbuf is not None:
             grad_zbuf = _lib.as_f32(grad_zbuf, "grad_zbuf")
-        grad_colours = torch.empty((P0 if shared_col else P, 3), dtype=torch.float32, device=dev)
+        shade = ctx.shading
+        # with fused shading the colour scatter fills a (P,3) scratch (d L / d shaded colour) that the shading backward
+        # turns into d albedo / d normal / d position
+        grad_colours = torch.empty((P if (shade is not None or not shared_col) else P0, 3), dtype=torch.float32, device=dev)
+        grad_normals = None
         # packed clouds: rows no view range covers are never written by the kernels
         grad_points = torch.empty_like(points_c) if shared else torch.zeros_like(points_c)
         a = _lib.RenderArgs()
@@ -163,6 +206,14 @@ class _RenderFunction(torch.autograd.Function):
         a.shared_colours = int(shared_col)
         a.grad_image, a.grad_zbuf = _lib.ptr(grad_image), _lib.ptr(grad_zbuf)
         a.grad_colours, a.grad_points_world = _lib.ptr(grad_colours), _lib.ptr(grad_points)
+        grad_albedo = grad_pshade = None
+        if shade is not None:
+            sh, normals_c, albedo_c = shade
+            grad_albedo, grad_normals, grad_pshade = (torch.empty((P0, 3), dtype=torch.float32, device=dev) for _ in range(3))
+            _fill_shading(a, sh, albedo_c)
+            a.normals_world = _lib.ptr(normals_c)
+            a.grad_albedo, a.grad_normals_world = _lib.ptr(grad_albedo), _lib.ptr(grad_normals)
+            a.grad_points_shading = _lib.ptr(grad_pshade)
         lib = _lib.load()
         with torch.cuda.device(dev):
             if grad_sync is None:
@@ -176,17 +227,27 @@ class _RenderFunction(torch.autograd.Function):
                 with torch.cuda.stream(side):
                     rc = lib.dss_colour_backward(_lib.ctx(dev), C.byref(a), _lib.stream_ptr(dev))
                     _lib.check(rc, "dss_colour_backward")
-                    grad_sync.reduce_early(grad_colours)
+                    if shade is not None:
+                        shade_done = torch.cuda.Event()
+                        shade_done.record(side)
+                        grad_sync.reduce_early(grad_albedo, grad_normals)
+                    else:
+                        grad_sync.reduce_early(grad_colours)
                 a.grad_colours = _lib.ptr(None)
                 rc = lib.dss_render_backward(_lib.ctx(dev), C.byref(a), _lib.stream_ptr(dev))
                 _lib.check(rc, "dss_render_backward")
+                if shade is not None:
+                    main.wait_event(shade_done)
+                    grad_points += grad_pshade           # position gradient through the shading
                 grad_sync.reduce_late(grad_points)
                 grad_sync.join(dev)
-        return (grad_points, None, grad_colours) + (None,) * 9
+        if shade is not None:
+            return (grad_points, grad_normals, grad_albedo) + (None,) * 10
+        return (grad_points, None, grad_colours) + (None,) * 10
 
 
 def render_points(points, normals, colours, proj, view, h, params: SplatParams, first_idx=None, num_points=None,
-                  shared_cloud=True, return_fragments=False, grad_sync=None) -> RenderOutput:
+                  shared_cloud=True, return_fragments=False, grad_sync=None, shading=None) -> RenderOutput:
     """Render ``N`` views of an oriented point cloud to RGBA.
 
     points, normals : (P0,3) when ``shared_cloud`` (one cloud seen from N cameras) else packed (P,3)
@@ -194,14 +255,27 @@ def render_points(points, normals, colours, proj, view, h, params: SplatParams, 
                       features used by every view of a shared cloud (gradient then summed over the views)
     proj, view      : (N,4,4) full-projection and world-to-view matrices, row-vector convention
     h               : (N,) per-view or (P,) per-splat variance scale (rasterizer.py:293-402)
+    shading         : optional Shading -- `colours` is then the per-point albedo (P0,3) and the colour of every
+                      (view, point) is computed in the preprocess kernel: albedo * (ambient + diffuse) + specular
+                      (DSS/core/texture.py:74-127); gradients flow to the albedo, the NORMALS and the positions
     grad_sync       : optional dss_b200.parallel.GradSync -- the backward then returns gradients already summed over the
                       ranks of a view-sharded step, the collectives overlapped with the backward kernels
     """
     outs = _RenderFunction.apply(points, normals, colours, proj, view, h, first_idx, num_points,
-                                 bool(shared_cloud), params, bool(return_fragments), grad_sync)
+                                 bool(shared_cloud), params, bool(return_fragments), grad_sync, shading)
     image, idx, weights, visible, records, scaler = outs[:6]
     zbuf, qvalue = (outs[6], outs[7]) if return_fragments else (None, None)
     return RenderOutput(image, idx, zbuf, qvalue, weights, visible, records, scaler)
+
+
+def make_shading(lights, view_matrices, shininess=64.0) -> Shading:
+    """Shading record for the fused route from a DirectionalLights / PointLights object (dss_b200.core.lighting) and the
+    (N,4,4) world-to-view matrices of the step's cameras."""
+    from .core.lighting import pack_lights
+    from .core.texture import camera_centres
+    rows, ambient, kind = pack_lights(lights)
+    dev = view_matrices.device
+    return Shading(rows.to(dev), ambient.to(dev), camera_centres(view_matrices).contiguous().float(), kind, float(shininess))
 
 
 def preprocess_points(points, normals, proj, view, h, params: SplatParams, first_idx=None, num_points=None,

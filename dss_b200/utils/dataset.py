@@ -1,7 +1,9 @@
 """``data_dict.npz`` of the multi-view reconstruction data (DSS/utils/dataset.py:30-211, written by
 scripts/create_mvr_data_from_mesh.py:170-255): the cloud in object coordinates and one 4x4 world-to-view matrix per
-image.  Image / mask / depth files need imageio and OpenEXR readers that are not part of this path; arrays already in
-memory can be attached instead.  Host-side and cold."""
+image, plus the ground-truth image and mask files next to it (dataset.py:36-101: every file of ``<data_dir>/image`` /
+``<data_dir>/mask`` with the configured extension, sorted; rgb -> (3,H,W) float32 in [0,1], mask -> (1,H,W) float 0/1),
+read with PIL (the reference uses imageio, which this image lacks).  ``pinned_batch`` stages a batch of views in pinned
+host memory for the step's host->device copy.  Dense depth maps (OpenEXR) are not read.  Host-side and cold."""
 import os
 
 import numpy as np
@@ -29,10 +31,25 @@ class MVRData:
     ``data[i]`` -> ``{"camera_mat": (4,4) f32 [, "img.rgb": (3,H,W), "img.mask": (1,H,W)]}`` like
     ``MVRDataset.__getitem__`` (dataset.py:171-211); images are only present when given to the constructor."""
 
-    def __init__(self, data_dir_or_file, data_dict="data_dict.npz", images=None, masks=None, n_imgs=None):
+    def __init__(self, data_dir_or_file, data_dict="data_dict.npz", images=None, masks=None, n_imgs=None,
+                 img_folder="image", mask_folder="mask", img_extension="png", mask_extension="png", load_images=True):
         path = data_dir_or_file
+        data_dir = None
         if os.path.isdir(path):
+            data_dir = path
             path = os.path.join(path, data_dict)
+        if load_images and data_dir is not None and images is None and masks is None:
+            # dataset.py:41-57: the files of the two folders with the configured extension, sorted by name
+            def listing(folder, ext):
+                d = os.path.join(data_dir, folder)
+                if not os.path.isdir(d):
+                    return None
+                return [os.path.join(d, f) for f in sorted(os.listdir(d)) if os.path.splitext(f)[1].lower()[1:] == ext]
+            self.image_files, self.mask_files = listing(img_folder, img_extension), listing(mask_folder, mask_extension)
+            if self.image_files:
+                images = self.load_all_images()
+            if self.mask_files:
+                masks = self.load_all_masks()
         self.data_dict = np.load(path, allow_pickle=True)
         if "camera_mat" not in self.data_dict:
             raise ValueError("data_dict must contain camera_mat!")
@@ -48,6 +65,40 @@ class MVRData:
 
     def __len__(self):
         return self.n_imgs
+
+    def load_all_images(self):
+        """dataset.py:88-93: (3,H,W) float32 tensors in [0,1], alpha dropped."""
+        from PIL import Image
+        out = []
+        for path in self.image_files:
+            rgb = np.asarray(Image.open(path).convert("RGB"), dtype=np.float32) / 255.0
+            out.append(torch.from_numpy(np.ascontiguousarray(rgb.transpose(2, 0, 1))))
+        return out
+
+    def load_all_masks(self):
+        """dataset.py:95-101: 8-bit grey -> bool -> (1,H,W) float32 0/1."""
+        from PIL import Image
+        out = []
+        for path in self.mask_files:
+            m = np.asarray(Image.open(path).convert("L")).astype(bool)[None]
+            out.append(torch.from_numpy(np.ascontiguousarray(m)).float())
+        return out
+
+    @property
+    def resolution(self):
+        return None if self.images is None else tuple(self.images[0].shape[1:])
+
+    def pinned_batch(self, indices):
+        """Views `indices` stacked in PINNED host memory, ready for one non-blocking copy per tensor:
+        {"camera_mat": (B,4,4) [, "img.rgb": (B,3,H,W), "img.mask": (B,1,H,W)]} (what a training step uploads)."""
+        idx = [int(i) % len(self) for i in indices]
+        pin = lambda t: t.pin_memory() if torch.cuda.is_available() else t
+        out = {"camera_mat": pin(torch.from_numpy(np.stack([self.camera_mat[i] for i in idx])))}
+        if self.images is not None:
+            out["img.rgb"] = pin(torch.stack([torch.as_tensor(self.images[i]) for i in idx]))
+        if self.masks is not None:
+            out["img.mask"] = pin(torch.stack([torch.as_tensor(self.masks[i]) for i in idx]))
+        return out
 
     def __getitem__(self, idx):
         idx = idx % len(self)

@@ -233,8 +233,31 @@ typedef struct dss_render_args {
      * colour, the common host-side input: the reference only materialises the (N*P0,3) tensor on the device, after
      * shading) and `grad_colours` is (P0,3), summed over the views. */
     int32_t shared_colours;
+    /* ---- per-point shading fused into the path (DSS/core/texture.py:74-127, lighting.py:10-172) ----
+     * shade != 0 (shared_cloud only): the per-(view,point) colours are COMPUTED instead of read from `colours`:
+     *   shaded = albedo * (ambient + sum_l Cd_l relu(n.d_l)) + sum_l Cs_l (relu(v.r_l) [n.d_l > 0])^shininess,
+     *   n = normalize(normal), d_l = normalize(direction_l) or normalize(location_l - p), v = normalize(cam - p),
+     *   r_l = -d_l + 2 (n.d_l) n          (all normalisations as F.normalize(eps = 1e-6))
+     * in the preprocess kernel (forward), and the backward turns the colour gradient into gradients w.r.t. the albedo,
+     * the NORMALS and (view direction, point lights) the positions -- what torch autograd does in the reference after
+     * ~40 ATen kernels on (N*P0,3) tensors. */
+    int32_t shade;
+    int32_t n_lights;              /* L, 1 .. DSS_MAX_LIGHTS                                       */
+    int32_t light_type;            /* 0: directional (rows of `lights` start with a direction), 1: point (a location) */
+    float shininess;               /* specular exponent (texture.py:76: 64)                        */
     int32_t reserved0;
+    const float *albedo;           /* (P0,3) per-point rgb                                         */
+    const float *lights;           /* (L,9) {direction | location, diffuse rgb, specular rgb}      */
+    const float *ambient;          /* (3,) ambient colour (summed over the lights' ambient terms)  */
+    const float *cam_centres;      /* (N,3) camera centres in world space                          */
+    float *shaded;                 /* (P,3) shaded colours: written by the forward, the blend reads them */
+    /* backward (shade): `grad_colours` is then a (P,3) SCRATCH that receives d L / d shaded; outputs: */
+    float *grad_albedo;            /* (P0,3) summed over views                                     */
+    float *grad_normals_world;     /* (P0,3) summed over views                                     */
+    float *grad_points_shading;    /* (P0,3) position gradient through the shading; dss_render_backward adds it to
+                                      grad_points_world when it ran the colour half itself (grad_colours != NULL) */
 } dss_render_args;
+#define DSS_MAX_LIGHTS 8
 
 /* preprocess -> bin -> rasterize + blend.  Never waits for the device in steady state: the tile-list buffer is sized
  * from the total the PREVIOUS call published; tiles whose list has outgrown it are rasterized from the records on the

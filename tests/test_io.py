@@ -73,3 +73,42 @@ def test_data_dict_cloud_and_cameras(tmp_path):
     assert len(one) == 1
     with pytest.raises(ValueError):
         MVRData(str(tmp_path), images=[0] * (V - 1))
+
+
+def test_mvr_data_reads_images_and_masks_like_the_reference(tmp_path):
+    """DSS/utils/dataset.py:36-101,171-211: files of <dir>/image and <dir>/mask (sorted, by extension), rgb (3,H,W) in
+    [0,1], mask (1,H,W) 0/1, one camera_mat per image; unequal counts are an error."""
+    import numpy as np
+    import torch
+    from PIL import Image
+    from dss_b200.utils.dataset import MVRData
+    rng = np.random.default_rng(0)
+    n, H, W = 3, 12, 16
+    (tmp_path / "image").mkdir()
+    (tmp_path / "mask").mkdir()
+    imgs, masks = [], []
+    for i in range(n):
+        a = rng.integers(0, 256, (H, W, 4), dtype=np.uint8)          # RGBA on disk: alpha is dropped (dataset.py:91)
+        m = (rng.random((H, W)) > 0.5).astype(np.uint8) * 255
+        Image.fromarray(a, "RGBA").save(tmp_path / "image" / ("%03d.png" % i))
+        Image.fromarray(m, "L").save(tmp_path / "mask" / ("%03d.png" % i))
+        imgs.append(a[..., :3].astype(np.float32).transpose(2, 0, 1) / 255.0)
+        masks.append((m > 0).astype(np.float32)[None])
+    (tmp_path / "image" / "notes.txt").write_text("ignored: wrong extension")
+    cams = np.tile(np.eye(4, dtype=np.float32), (n, 1, 1))
+    cams[:, 3, 2] = [1.5, 2.0, 2.5]
+    np.savez(tmp_path / "data_dict.npz", camera_mat=cams, points=rng.random((10, 3)), normals=rng.random((10, 3)))
+    data = MVRData(str(tmp_path))
+    assert len(data) == n and data.resolution == (H, W)
+    for i in range(n):
+        item = data[i]
+        assert item["img.rgb"].shape == (3, H, W) and item["img.mask"].shape == (1, H, W)
+        np.testing.assert_allclose(item["img.rgb"].numpy(), imgs[i], atol=1e-7)
+        np.testing.assert_array_equal(item["img.mask"].numpy(), masks[i])
+        np.testing.assert_array_equal(item["camera_mat"], cams[i])
+    batch = data.pinned_batch([2, 0])
+    assert batch["img.rgb"].shape == (2, 3, H, W) and batch["camera_mat"].shape == (2, 4, 4)
+    np.testing.assert_allclose(batch["img.rgb"][0].numpy(), imgs[2], atol=1e-7)
+    (tmp_path / "mask" / "002.png").unlink()
+    with pytest.raises(ValueError, match="unequal number"):
+        MVRData(str(tmp_path))
