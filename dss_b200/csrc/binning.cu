@@ -51,23 +51,47 @@ int pack_records(dss_ctx *ctx, const float *points, const float *radii, const fl
 struct EdgeCtx {
     int bin, S, B;
     float inv_S, half_pix;
+    const float *tlo, *thi;   // optional tables of the B lower / upper bin edges (shared memory), or nullptr
 };
-__device__ __forceinline__ EdgeCtx make_edge_ctx(int bin, int S, int B) {
+__device__ __forceinline__ EdgeCtx make_edge_ctx(int bin, int S, int B, const float *tlo = nullptr, const float *thi = nullptr) {
     EdgeCtx e;
     e.bin = bin;
     e.S = S;
     e.B = B;
     e.inv_S = 1.0f / (float)S;
     e.half_pix = 1.0f / S;
+    e.tlo = tlo;
+    e.thi = thi;
     return e;
 }
 template <bool POW2>
-__device__ __forceinline__ float bin_lo_edge(int b, const EdgeCtx &e) {
+__device__ __forceinline__ float bin_lo_edge_eval(int b, const EdgeCtx &e) {
     return pix_to_ndc_fast(b * e.bin, e.S, e.inv_S, POW2) - e.half_pix;
 }
 template <bool POW2>
-__device__ __forceinline__ float bin_hi_edge(int b, const EdgeCtx &e) {
+__device__ __forceinline__ float bin_hi_edge_eval(int b, const EdgeCtx &e) {
     return pix_to_ndc_fast((b + 1) * e.bin - 1, e.S, e.inv_S, POW2) + e.half_pix;
+}
+// The exact-predicate fix-up evaluates ~12 edges per splat; with the edges of the B bins tabulated once per block (the
+// very same float values) that is 12 shared-memory loads instead of 12 x (IMAD, I2F, FFMA, FADD ...): the edge
+// arithmetic was 56 % of bin_count_kernel's instructions (profiles/r02_ncu_bin_count.txt).
+template <bool POW2>
+__device__ __forceinline__ float bin_lo_edge(int b, const EdgeCtx &e) {
+    return e.tlo ? e.tlo[b] : bin_lo_edge_eval<POW2>(b, e);
+}
+template <bool POW2>
+__device__ __forceinline__ float bin_hi_edge(int b, const EdgeCtx &e) {
+    return e.thi ? e.thi[b] : bin_hi_edge_eval<POW2>(b, e);
+}
+// fills the two tables (B <= BIN_EDGE_TABLE entries each); the caller synchronises
+constexpr int BIN_EDGE_TABLE = 128;
+template <bool POW2>
+__device__ __forceinline__ void fill_edge_tables(float *tlo, float *thi, int bin, int S, int B) {
+    const EdgeCtx e = make_edge_ctx(bin, S, B);
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        tlo[b] = bin_lo_edge_eval<POW2>(b, e);
+        thi[b] = bin_hi_edge_eval<POW2>(b, e);
+    }
 }
 
 template <bool POW2>
@@ -94,7 +118,8 @@ struct BinRect {
 };
 
 template <bool POW2>
-__device__ __forceinline__ BinRect splat_bin_rect(const float4 A, const float ry, int bin, int S, int B) {
+__device__ __forceinline__ BinRect splat_bin_rect(const float4 A, const float ry, int bin, int S, int B,
+                                                  const float *tlo = nullptr, const float *thi = nullptr) {
     BinRect r;
     r.empty = true;
     r.x0 = r.y0 = 0;
@@ -102,7 +127,7 @@ __device__ __forceinline__ BinRect splat_bin_rect(const float4 A, const float ry
     if (A.z < 0) return r;  // behind the camera (rasterize_points.cu:351-352); also NaN-safe below
     const float px0 = A.x - A.w, px1 = A.x + A.w;
     const float py0 = A.y - ry, py1 = A.y + ry;
-    const EdgeCtx e = make_edge_ctx(bin, S, B);
+    const EdgeCtx e = make_edge_ctx(bin, S, B, tlo, thi);
     bin_range<POW2>(py0, py1, e, r.y0, r.y1);
     if (r.y0 > r.y1) return r;
     bin_range<POW2>(px0, px1, e, r.x0, r.x1);
@@ -194,8 +219,9 @@ template <bool SMEM, bool POW2>
 __global__ void __launch_bounds__(BIN_THREADS)
 bin_count_kernel(const float4 *__restrict__ rec, const int64_t *__restrict__ first_idx,
                  const int64_t *__restrict__ num_points, int64_t P0_shared, int S, int bin, int B, int NS,
-                 const float *__restrict__ zrange, int32_t *__restrict__ counts) {
+                 const float *__restrict__ zrange, int32_t *__restrict__ counts, unsigned int *__restrict__ rects) {
     extern __shared__ int32_t s_hist[];
+    __shared__ float s_tlo[BIN_EDGE_TABLE], s_thi[BIN_EDGE_TABLE];
     const int n = blockIdx.y;
     const int nt = B * B * NS;
     const SliceMap sm = make_slice_map(zrange, n, NS);
@@ -203,10 +229,13 @@ bin_count_kernel(const float4 *__restrict__ rec, const int64_t *__restrict__ fir
     const int64_t chunk0 = (int64_t)blockIdx.x * BIN_CHUNK;
     if (chunk0 >= vr.count) return;
     int32_t *cnt = counts + (int64_t)n * nt;
+    const bool tab = B <= BIN_EDGE_TABLE;
+    if (tab) fill_edge_tables<POW2>(s_tlo, s_thi, bin, S, B);
     if (SMEM) {
         for (int t = threadIdx.x; t < nt; t += BIN_THREADS) s_hist[t] = 0;
-        __syncthreads();
     }
+    __syncthreads();
+    const float *tlo = tab ? s_tlo : nullptr, *thi = tab ? s_thi : nullptr;
 #pragma unroll 2
     for (int j = 0; j < BIN_ITEMS; ++j) {
         const int64_t i = chunk0 + j * BIN_THREADS + threadIdx.x;
@@ -214,9 +243,11 @@ bin_count_kernel(const float4 *__restrict__ rec, const int64_t *__restrict__ fir
         const int64_t p = vr.first + i;
         const float4 A = __ldg(&rec[2 * p]);
         const float ry = __ldg(&rec[2 * p + 1]).x;
-        const BinRect r = splat_bin_rect<POW2>(A, ry, bin, S, B);
+        const BinRect r = splat_bin_rect<POW2>(A, ry, bin, S, B, tlo, thi);
+        const int sl = r.empty ? 0 : depth_slice(sm, A.z);
+        // the scatter pass reuses the rectangle instead of deriving it again (and never touches the records)
+        if (rects) rects[p] = pack_rect(r, sl);
         if (r.empty) continue;
-        const int sl = depth_slice(sm, A.z);
         for (int by = r.y0; by <= r.y1; ++by)
             for (int bx = r.x0; bx <= r.x1; ++bx) {
                 const int key = (by * B + bx) * NS + sl;
@@ -238,8 +269,9 @@ __global__ void __launch_bounds__(BIN_THREADS)
 bin_scatter_kernel(const float4 *__restrict__ rec, const int64_t *__restrict__ first_idx,
                    const int64_t *__restrict__ num_points, int64_t P0_shared, int S, int bin, int B, int NS,
                    const float *__restrict__ zrange, int32_t *__restrict__ cursors, int32_t *__restrict__ ids,
-                   int ids_capacity) {
+                   int ids_capacity, const unsigned int *__restrict__ rects) {
     extern __shared__ int32_t s_hist[];
+    __shared__ float s_tlo[BIN_EDGE_TABLE], s_thi[BIN_EDGE_TABLE];
     const int n = blockIdx.y;
     const int nt = B * B * NS;
     const SliceMap sm = make_slice_map(zrange, n, NS);
@@ -247,10 +279,13 @@ bin_scatter_kernel(const float4 *__restrict__ rec, const int64_t *__restrict__ f
     const int64_t chunk0 = (int64_t)blockIdx.x * BIN_CHUNK;
     if (chunk0 >= vr.count) return;
     int32_t *cur = cursors + (int64_t)n * nt;
+    const bool tab = B <= BIN_EDGE_TABLE && !(SMEM && rects);
+    if (tab) fill_edge_tables<POW2>(s_tlo, s_thi, bin, S, B);
     if (SMEM) {
         for (int t = threadIdx.x; t < nt; t += BIN_THREADS) s_hist[t] = 0;
-        __syncthreads();
     }
+    __syncthreads();
+    const float *tlo = tab ? s_tlo : nullptr, *thi = tab ? s_thi : nullptr;
     unsigned int rect[SMEM ? BIN_ITEMS : 1];
 #pragma unroll
     for (int j = 0; j < BIN_ITEMS; ++j) {
@@ -258,9 +293,20 @@ bin_scatter_kernel(const float4 *__restrict__ rec, const int64_t *__restrict__ f
         const int64_t i = chunk0 + j * BIN_THREADS + threadIdx.x;
         if (i < vr.count) {
             const int64_t p = vr.first + i;
+            if (SMEM && rects) {
+                // rectangle + slice packed by the count pass: no record load, no edge arithmetic
+                const unsigned int pr = __ldg(&rects[p]);
+                rect[j] = pr;
+                if (pr != BIN_PACK_EMPTY) {
+                    const int x0 = pr & 127, x1 = (pr >> 7) & 127, y0 = (pr >> 14) & 127, y1 = (pr >> 21) & 127, sl = pr >> 28;
+                    for (int by = y0; by <= y1; ++by)
+                        for (int bx = x0; bx <= x1; ++bx) atomicAdd(&s_hist[(by * B + bx) * NS + sl], 1);
+                }
+                continue;
+            }
             const float4 A = __ldg(&rec[2 * p]);
             const float ry = __ldg(&rec[2 * p + 1]).x;
-            const BinRect r = splat_bin_rect<POW2>(A, ry, bin, S, B);
+            const BinRect r = splat_bin_rect<POW2>(A, ry, bin, S, B, tlo, thi);
             if (!r.empty) {
                 const int sl = depth_slice(sm, A.z);
                 if (SMEM) rect[j] = pack_rect(r, sl);
@@ -327,7 +373,7 @@ int choose_depth_slices(int B) {
 // count + scan.  counts / offsets have N*B*B*NS + 1 entries (the last count stays 0).
 int bin_count_and_scan(dss_ctx *ctx, const float4 *rec, const int64_t *first_idx, const int64_t *num_points,
                        int N, int64_t P0, int S, int bin, int NS, const float *zrange, int32_t *counts,
-                       int32_t *offsets, cudaStream_t st) {
+                       int32_t *offsets, unsigned int *rects, cudaStream_t st) {
     const int B = 1 + (S - 1) / bin;
     const int64_t nb = (int64_t)N * B * B * NS;
     DSS_CUDA_TRY(cudaMemsetAsync(counts, 0, (size_t)(nb + 1) * sizeof(int32_t), st));
@@ -340,13 +386,13 @@ int bin_count_and_scan(dss_ctx *ctx, const float4 *rec, const int64_t *first_idx
             int rc = pow2 ? prepare_smem(bin_count_kernel<true, true>, smem) : prepare_smem(bin_count_kernel<true, false>, smem);
             if (rc) return rc;
             if (pow2)
-                bin_count_kernel<true, true><<<grid, BIN_THREADS, smem, st>>>(rec, first_idx, num_points, P0, S, bin, B, NS, zrange, counts);
+                bin_count_kernel<true, true><<<grid, BIN_THREADS, smem, st>>>(rec, first_idx, num_points, P0, S, bin, B, NS, zrange, counts, rects);
             else
-                bin_count_kernel<true, false><<<grid, BIN_THREADS, smem, st>>>(rec, first_idx, num_points, P0, S, bin, B, NS, zrange, counts);
+                bin_count_kernel<true, false><<<grid, BIN_THREADS, smem, st>>>(rec, first_idx, num_points, P0, S, bin, B, NS, zrange, counts, rects);
         } else if (pow2) {
-            bin_count_kernel<false, true><<<grid, BIN_THREADS, 0, st>>>(rec, first_idx, num_points, P0, S, bin, B, NS, zrange, counts);
+            bin_count_kernel<false, true><<<grid, BIN_THREADS, 0, st>>>(rec, first_idx, num_points, P0, S, bin, B, NS, zrange, counts, nullptr);
         } else {
-            bin_count_kernel<false, false><<<grid, BIN_THREADS, 0, st>>>(rec, first_idx, num_points, P0, S, bin, B, NS, zrange, counts);
+            bin_count_kernel<false, false><<<grid, BIN_THREADS, 0, st>>>(rec, first_idx, num_points, P0, S, bin, B, NS, zrange, counts, nullptr);
         }
         DSS_LAUNCH_CHECK(ctx);
     }
@@ -355,7 +401,7 @@ int bin_count_and_scan(dss_ctx *ctx, const float4 *rec, const int64_t *first_idx
 
 int bin_scatter(dss_ctx *ctx, const float4 *rec, const int64_t *first_idx, const int64_t *num_points, int N,
                 int64_t P0, int S, int bin, int NS, const float *zrange, const int32_t *offsets, int32_t *cursors,
-                int32_t *ids, int64_t ids_capacity, cudaStream_t st) {
+                int32_t *ids, int64_t ids_capacity, const unsigned int *rects, cudaStream_t st) {
     const int B = 1 + (S - 1) / bin;
     const int64_t nb = (int64_t)N * B * B * NS;
     const int cap = (int)(ids_capacity > (int64_t)INT32_MAX ? (int64_t)INT32_MAX : ids_capacity);
@@ -369,13 +415,13 @@ int bin_scatter(dss_ctx *ctx, const float4 *rec, const int64_t *first_idx, const
             int rc = pow2 ? prepare_smem(bin_scatter_kernel<true, true>, smem) : prepare_smem(bin_scatter_kernel<true, false>, smem);
             if (rc) return rc;
             if (pow2)
-                bin_scatter_kernel<true, true><<<grid, BIN_THREADS, smem, st>>>(rec, first_idx, num_points, P0, S, bin, B, NS, zrange, cursors, ids, cap);
+                bin_scatter_kernel<true, true><<<grid, BIN_THREADS, smem, st>>>(rec, first_idx, num_points, P0, S, bin, B, NS, zrange, cursors, ids, cap, rects);
             else
-                bin_scatter_kernel<true, false><<<grid, BIN_THREADS, smem, st>>>(rec, first_idx, num_points, P0, S, bin, B, NS, zrange, cursors, ids, cap);
+                bin_scatter_kernel<true, false><<<grid, BIN_THREADS, smem, st>>>(rec, first_idx, num_points, P0, S, bin, B, NS, zrange, cursors, ids, cap, rects);
         } else if (pow2) {
-            bin_scatter_kernel<false, true><<<grid, BIN_THREADS, 0, st>>>(rec, first_idx, num_points, P0, S, bin, B, NS, zrange, cursors, ids, cap);
+            bin_scatter_kernel<false, true><<<grid, BIN_THREADS, 0, st>>>(rec, first_idx, num_points, P0, S, bin, B, NS, zrange, cursors, ids, cap, nullptr);
         } else {
-            bin_scatter_kernel<false, false><<<grid, BIN_THREADS, 0, st>>>(rec, first_idx, num_points, P0, S, bin, B, NS, zrange, cursors, ids, cap);
+            bin_scatter_kernel<false, false><<<grid, BIN_THREADS, 0, st>>>(rec, first_idx, num_points, P0, S, bin, B, NS, zrange, cursors, ids, cap, nullptr);
         }
         DSS_LAUNCH_CHECK(ctx);
     }
@@ -472,7 +518,7 @@ int dss_rasterize_coarse(dss_ctx *ctx, const float *points, const float *radii, 
     if ((rc = ctx_get(ctx, BUF_RECORDS, (size_t)(2 * (P > 0 ? P : 1)), &rec))) return rc;
     if ((rc = ctx_get(ctx, BUF_TILE_COUNTS, (size_t)(nb + 1), &counts))) return rc;
     if ((rc = pack_records(ctx, points, radii, nullptr, P, rec, st))) return rc;
-    if ((rc = bin_count_and_scan(ctx, rec, first_idx, num_points, N, P, S, bin_size, 1, nullptr, counts, bin_offsets, st)))
+    if ((rc = bin_count_and_scan(ctx, rec, first_idx, num_points, N, P, S, bin_size, 1, nullptr, counts, bin_offsets, nullptr, st)))
         return rc;
     if ((rc = publish_words(ctx, bin_offsets + nb, ctx->h_pinned, 1, st))) return rc;
     DSS_CUDA_TRY(cudaStreamSynchronize(st));
@@ -484,7 +530,7 @@ int dss_rasterize_coarse(dss_ctx *ctx, const float *points, const float *radii, 
     }
     if (total == 0) return DSS_OK;
     return bin_scatter(ctx, rec, first_idx, num_points, N, P, S, bin_size, 1, nullptr, bin_offsets, counts, bin_ids,
-                       bin_ids_capacity, st);
+                       bin_ids_capacity, nullptr, st);
 }
 
 }  // extern "C"

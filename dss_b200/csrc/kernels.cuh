@@ -22,13 +22,15 @@ int init_zrange(dss_ctx *ctx, float *zrange, int N, cudaStream_t st);
 int compute_zrange(dss_ctx *ctx, const float4 *rec, const int64_t *first_idx, const int64_t *num_points, int N,
                    int64_t P0, float *zrange, cudaStream_t st);
 
+// rects (optional, one word per packed splat): the count pass stores every splat's tile rectangle + depth slice there and
+// the scatter pass, given the same array, reuses them instead of deriving them again from the records
 int bin_count_and_scan(dss_ctx *ctx, const float4 *rec, const int64_t *first_idx, const int64_t *num_points,
                        int N, int64_t P0, int S, int bin, int NS, const float *zrange, int32_t *counts,
-                       int32_t *offsets, cudaStream_t st);
+                       int32_t *offsets, unsigned int *rects, cudaStream_t st);
 
 int bin_scatter(dss_ctx *ctx, const float4 *rec, const int64_t *first_idx, const int64_t *num_points, int N,
                 int64_t P0, int S, int bin, int NS, const float *zrange, const int32_t *offsets, int32_t *cursors,
-                int32_t *ids, int64_t ids_capacity, cudaStream_t st);
+                int32_t *ids, int64_t ids_capacity, const unsigned int *rects, cudaStream_t st);
 
 // Depth slicing shared by the binning and raster kernels (identical arithmetic on both sides).
 struct SliceMap {

@@ -712,8 +712,15 @@ int bin_and_raster(dss_ctx *ctx, RasterArgs a, const int64_t *first_idx, const i
         if ((rc = compute_zrange(ctx, a.rec, first_idx, num_points, a.N, P0, zrange, st))) return rc;
     }
     a.zrange = zrange;
+    // (the packed rectangle needs B <= 128 tiles per side and <= 16 slices, like the block histograms)
+    unsigned int *rects = nullptr;
+    {
+        const int64_t Ptot = (first_idx == nullptr) ? (int64_t)a.N * P0 : P0;
+        if (a.B <= 128 && a.NS <= 16 && (int64_t)a.B * a.B * a.NS <= 48 * 1024 && !ctx->bin_direct && Ptot > 0)
+            if ((rc = ctx_get(ctx, BUF_BIN_RECTS, (size_t)Ptot, &rects))) return rc;
+    }
     if ((rc = bin_count_and_scan(ctx, a.rec, first_idx, num_points, a.N, P0, S, RASTER_TILE, a.NS, zrange, counts,
-                                 offsets, st)))
+                                 offsets, rects, st)))
         return rc;
     a.tile_offsets = offsets;
     a.stats = nullptr;
@@ -759,7 +766,7 @@ int bin_and_raster(dss_ctx *ctx, RasterArgs a, const int64_t *first_idx, const i
         return DSS_E_CAPACITY;
     }
     if ((rc = bin_scatter(ctx, a.rec, first_idx, num_points, a.N, P0, S, RASTER_TILE, a.NS, zrange, offsets, counts, ids,
-                          a.ids_capacity, st)))
+                          a.ids_capacity, rects, st)))
         return rc;
     a.tile_ids = ids;
     if ((rc = raster_forward(ctx, a, st))) return rc;
