@@ -51,17 +51,14 @@ int pack_records(dss_ctx *ctx, const float *points, const float *radii, const fl
 struct EdgeCtx {
     int bin, S, B;
     float inv_S, half_pix;
-    const float *tlo, *thi;   // optional tables of the B lower / upper bin edges (shared memory), or nullptr
 };
-__device__ __forceinline__ EdgeCtx make_edge_ctx(int bin, int S, int B, const float *tlo = nullptr, const float *thi = nullptr) {
+__device__ __forceinline__ EdgeCtx make_edge_ctx(int bin, int S, int B) {
     EdgeCtx e;
     e.bin = bin;
     e.S = S;
     e.B = B;
     e.inv_S = 1.0f / (float)S;
     e.half_pix = 1.0f / S;
-    e.tlo = tlo;
-    e.thi = thi;
     return e;
 }
 template <bool POW2>
@@ -72,27 +69,13 @@ template <bool POW2>
 __device__ __forceinline__ float bin_hi_edge_eval(int b, const EdgeCtx &e) {
     return pix_to_ndc_fast((b + 1) * e.bin - 1, e.S, e.inv_S, POW2) + e.half_pix;
 }
-// The exact-predicate fix-up evaluates ~12 edges per splat; with the edges of the B bins tabulated once per block (the
-// very same float values) that is 12 shared-memory loads instead of 12 x (IMAD, I2F, FFMA, FADD ...): the edge
-// arithmetic was 56 % of bin_count_kernel's instructions (profiles/r02_ncu_bin_count.txt).
 template <bool POW2>
-__device__ __forceinline__ float bin_lo_edge(int b, const EdgeCtx &e) {
-    return e.tlo ? e.tlo[b] : bin_lo_edge_eval<POW2>(b, e);
-}
+__device__ __forceinline__ float bin_lo_edge(int b, const EdgeCtx &e) { return bin_lo_edge_eval<POW2>(b, e); }
 template <bool POW2>
-__device__ __forceinline__ float bin_hi_edge(int b, const EdgeCtx &e) {
-    return e.thi ? e.thi[b] : bin_hi_edge_eval<POW2>(b, e);
-}
-// fills the two tables (B <= BIN_EDGE_TABLE entries each); the caller synchronises
-constexpr int BIN_EDGE_TABLE = 128;
-template <bool POW2>
-__device__ __forceinline__ void fill_edge_tables(float *tlo, float *thi, int bin, int S, int B) {
-    const EdgeCtx e = make_edge_ctx(bin, S, B);
-    for (int b = threadIdx.x; b < B; b += blockDim.x) {
-        tlo[b] = bin_lo_edge_eval<POW2>(b, e);
-        thi[b] = bin_hi_edge_eval<POW2>(b, e);
-    }
-}
+__device__ __forceinline__ float bin_hi_edge(int b, const EdgeCtx &e) { return bin_hi_edge_eval<POW2>(b, e); }
+// (measured and dropped, round 2: the B edges tabulated once per block in shared memory -- the same float values, 12 loads
+//  instead of 12 x (IMAD, I2F, FFMA, FADD) per splat: bin_count unchanged at 0.125 ms, bin_scatter 0.18 -> 0.27 ms; the
+//  fix-up loops are latency chains either way and the table reads went through generic loads)
 
 template <bool POW2>
 __device__ __forceinline__ void bin_range(float p0, float p1, const EdgeCtx &e, int &lo, int &hi) {
@@ -118,8 +101,7 @@ struct BinRect {
 };
 
 template <bool POW2>
-__device__ __forceinline__ BinRect splat_bin_rect(const float4 A, const float ry, int bin, int S, int B,
-                                                  const float *tlo = nullptr, const float *thi = nullptr) {
+__device__ __forceinline__ BinRect splat_bin_rect(const float4 A, const float ry, int bin, int S, int B) {
     BinRect r;
     r.empty = true;
     r.x0 = r.y0 = 0;
@@ -127,7 +109,7 @@ __device__ __forceinline__ BinRect splat_bin_rect(const float4 A, const float ry
     if (A.z < 0) return r;  // behind the camera (rasterize_points.cu:351-352); also NaN-safe below
     const float px0 = A.x - A.w, px1 = A.x + A.w;
     const float py0 = A.y - ry, py1 = A.y + ry;
-    const EdgeCtx e = make_edge_ctx(bin, S, B, tlo, thi);
+    const EdgeCtx e = make_edge_ctx(bin, S, B);
     bin_range<POW2>(py0, py1, e, r.y0, r.y1);
     if (r.y0 > r.y1) return r;
     bin_range<POW2>(px0, px1, e, r.x0, r.x1);
@@ -221,7 +203,6 @@ bin_count_kernel(const float4 *__restrict__ rec, const int64_t *__restrict__ fir
                  const int64_t *__restrict__ num_points, int64_t P0_shared, int S, int bin, int B, int NS,
                  const float *__restrict__ zrange, int32_t *__restrict__ counts, unsigned int *__restrict__ rects) {
     extern __shared__ int32_t s_hist[];
-    __shared__ float s_tlo[BIN_EDGE_TABLE], s_thi[BIN_EDGE_TABLE];
     const int n = blockIdx.y;
     const int nt = B * B * NS;
     const SliceMap sm = make_slice_map(zrange, n, NS);
@@ -229,13 +210,10 @@ bin_count_kernel(const float4 *__restrict__ rec, const int64_t *__restrict__ fir
     const int64_t chunk0 = (int64_t)blockIdx.x * BIN_CHUNK;
     if (chunk0 >= vr.count) return;
     int32_t *cnt = counts + (int64_t)n * nt;
-    const bool tab = B <= BIN_EDGE_TABLE;
-    if (tab) fill_edge_tables<POW2>(s_tlo, s_thi, bin, S, B);
     if (SMEM) {
         for (int t = threadIdx.x; t < nt; t += BIN_THREADS) s_hist[t] = 0;
+        __syncthreads();
     }
-    __syncthreads();
-    const float *tlo = tab ? s_tlo : nullptr, *thi = tab ? s_thi : nullptr;
 #pragma unroll 2
     for (int j = 0; j < BIN_ITEMS; ++j) {
         const int64_t i = chunk0 + j * BIN_THREADS + threadIdx.x;
@@ -243,7 +221,7 @@ bin_count_kernel(const float4 *__restrict__ rec, const int64_t *__restrict__ fir
         const int64_t p = vr.first + i;
         const float4 A = __ldg(&rec[2 * p]);
         const float ry = __ldg(&rec[2 * p + 1]).x;
-        const BinRect r = splat_bin_rect<POW2>(A, ry, bin, S, B, tlo, thi);
+        const BinRect r = splat_bin_rect<POW2>(A, ry, bin, S, B);
         const int sl = r.empty ? 0 : depth_slice(sm, A.z);
         // the scatter pass reuses the rectangle instead of deriving it again (and never touches the records)
         if (rects) rects[p] = pack_rect(r, sl);
@@ -271,7 +249,6 @@ bin_scatter_kernel(const float4 *__restrict__ rec, const int64_t *__restrict__ f
                    const float *__restrict__ zrange, int32_t *__restrict__ cursors, int32_t *__restrict__ ids,
                    int ids_capacity, const unsigned int *__restrict__ rects) {
     extern __shared__ int32_t s_hist[];
-    __shared__ float s_tlo[BIN_EDGE_TABLE], s_thi[BIN_EDGE_TABLE];
     const int n = blockIdx.y;
     const int nt = B * B * NS;
     const SliceMap sm = make_slice_map(zrange, n, NS);
@@ -279,13 +256,10 @@ bin_scatter_kernel(const float4 *__restrict__ rec, const int64_t *__restrict__ f
     const int64_t chunk0 = (int64_t)blockIdx.x * BIN_CHUNK;
     if (chunk0 >= vr.count) return;
     int32_t *cur = cursors + (int64_t)n * nt;
-    const bool tab = B <= BIN_EDGE_TABLE && !(SMEM && rects);
-    if (tab) fill_edge_tables<POW2>(s_tlo, s_thi, bin, S, B);
     if (SMEM) {
         for (int t = threadIdx.x; t < nt; t += BIN_THREADS) s_hist[t] = 0;
+        __syncthreads();
     }
-    __syncthreads();
-    const float *tlo = tab ? s_tlo : nullptr, *thi = tab ? s_thi : nullptr;
     unsigned int rect[SMEM ? BIN_ITEMS : 1];
 #pragma unroll
     for (int j = 0; j < BIN_ITEMS; ++j) {
@@ -306,7 +280,7 @@ bin_scatter_kernel(const float4 *__restrict__ rec, const int64_t *__restrict__ f
             }
             const float4 A = __ldg(&rec[2 * p]);
             const float ry = __ldg(&rec[2 * p + 1]).x;
-            const BinRect r = splat_bin_rect<POW2>(A, ry, bin, S, B, tlo, thi);
+            const BinRect r = splat_bin_rect<POW2>(A, ry, bin, S, B);
             if (!r.empty) {
                 const int sl = depth_slice(sm, A.z);
                 if (SMEM) rect[j] = pack_rect(r, sl);

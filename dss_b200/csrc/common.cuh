@@ -108,6 +108,7 @@ struct dss_ctx {
     int ns_override;    // tuning (env DSS_NS): number of depth slices of the forward tile lists, 0 = automatic
     int no_tile_order;  // tuning (env DSS_NO_TILE_ORDER=1): launch the raster tiles in index order
     int occ_tilebin;    // tuning (env DSS_OCC_TILEBIN=1): bin the backward's visible splats by tile only (unordered lists)
+    int bin_no_rects;   // tuning (env DSS_BIN_NORECTS=1): the scatter pass derives the tile rectangles again
     int bin_direct;     // tuning (env DSS_BIN_DIRECT): tile binning with plain global atomics instead of per-block histograms
     double stage_ms[dss::NUM_STAGES];
     int64_t stage_calls[dss::NUM_STAGES];

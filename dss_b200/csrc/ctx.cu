@@ -281,6 +281,8 @@ int dss_create(dss_ctx **out) {
     {
         const char *e = getenv("DSS_BIN_DIRECT");
         c->bin_direct = (e && e[0] == '1') ? 1 : 0;
+        const char *nr = getenv("DSS_BIN_NORECTS");
+        c->bin_no_rects = (nr && nr[0] == '1') ? 1 : 0;
         const char *mb = getenv("DSS_RASTER_MINB");
         c->raster_minb5 = (mb && mb[0] == '5') ? 1 : 0;
         const char *sf = getenv("DSS_SYNC_FORWARD");
