@@ -405,7 +405,6 @@ __global__ void __launch_bounds__(RASTER_THREADS, MINB)
 raster_sliced_kernel(const __grid_constant__ RasterArgs a) {
     __shared__ unsigned long long s_keys[RASTER_THREADS * KMAX];   // [pixel][k]
     __shared__ int s_queue[RASTER_QCAP];
-    __shared__ unsigned int s_qrect[RASTER_QCAP];   // exact pixel rectangle of every queued survivor (tile-local, 4 x 4 bits)
     __shared__ unsigned long long s_pend_key[RASTER_THREADS / 32][RASTER_WPEND];   // per warp: accepted fragments
     __shared__ unsigned short s_pend_pix[RASTER_THREADS / 32][RASTER_WPEND];       //           waiting for insertion
     __shared__ float s_xf[RASTER_TILE], s_yf[RASTER_TILE];   // exact pixel centres of the tile
@@ -489,21 +488,18 @@ raster_sliced_kernel(const __grid_constant__ RasterArgs a) {
                     pA = __ldg(&a.rec[2 * (int64_t)id0]);
                     pry = __ldg(&a.rec[2 * (int64_t)id0 + 1]).x;
                 }
-                unsigned int rect = 0;
                 if (j < end) {
                     if (STATS) st_scanned++;
                     if (A.z >= 0.0f) {
-                        // exact pixel rectangle (the pixels that pass the reference's bounding-box test), clipped to the tile
-                        int x0, x1, y0, y1;
-                        pixel_range(A.x, A.w, tx0, tx1, S, inv_S, pow2, half_S, x0, x1);
-                        pixel_range(A.y, ry, ty0, ty1, S, inv_S, pow2, half_S, y0, y1);
+                        const int x0 = max(tx0, (int)fmaxf(ceilf((A.x - A.w + 1.0f) * half_S - 0.5f) - 1.0f, -1.0f));
+                        const int x1 = min(tx1, (int)fminf(floorf((A.x + A.w + 1.0f) * half_S - 0.5f) + 1.0f, (float)S));
+                        const int y0 = max(ty0, (int)fmaxf(ceilf((A.y - ry + 1.0f) * half_S - 0.5f) - 1.0f, -1.0f));
+                        const int y1 = min(ty1, (int)fminf(floorf((A.y + ry + 1.0f) * half_S - 0.5f) + 1.0f, (float)S));
                         if (x0 <= x1 && y0 <= y1) {
                             unsigned int zb = 0;
                             for (int by = (y0 - ty0) >> 2; by <= (y1 - ty0) >> 2; ++by)
                                 for (int bx = (x0 - tx0) >> 2; bx <= (x1 - tx0) >> 2; ++bx) zb = max(zb, s_blk[by * 4 + bx]);
                             survive = __float_as_uint(A.z + 0.0f) <= zb;
-                            rect = (unsigned int)(x0 - tx0) | ((unsigned int)(y0 - ty0) << 4) | ((unsigned int)(x1 - tx0) << 8) |
-                                   ((unsigned int)(y1 - ty0) << 12);
                         }
                     }
                 }
@@ -512,9 +508,7 @@ raster_sliced_kernel(const __grid_constant__ RasterArgs a) {
                 if (lane == 0 && m) wbase = atomicAdd(&s_qcount, __popc(m));
                 wbase = __shfl_sync(FULL, wbase, 0);
                 if (survive) {
-                    const int slot = wbase + __popc(m & ((1u << lane) - 1u));
-                    s_queue[slot] = id;
-                    s_qrect[slot] = rect;
+                    s_queue[wbase + __popc(m & ((1u << lane) - 1u))] = id;
                     if (STATS) st_surv++;
                 }
                 base += RASTER_THREADS;
@@ -524,50 +518,35 @@ raster_sliced_kernel(const __grid_constant__ RasterArgs a) {
             __syncthreads();   // everyone has read nq before the next chunk's appends can change it
             if (more && nq <= RASTER_QCAP - RASTER_THREADS && base < end) continue;   // keep filling
             if (nq > 0) {
-                // ---- phase 2: rasterize the queued survivors.  Every warp owns a contiguous share of the queue; every
-                //      LANE walks the pixel rectangle of one survivor (row-major) and takes the next survivor of the
-                //      warp's share the moment its rectangle is done, so the lanes stay busy whatever the sizes of the
-                //      rectangles (one survivor per lane with the warp's largest rectangle as common trip count ran
-                //      the loop at 46 % lane utilisation: clipped rectangles are 1..30 pixels).  Accepted fragments go
-                //      to the warp's own buffer (no atomics, no election: the fill level is a warp-uniform register)
-                //      and are inserted 32 at a time when it runs full ----
-                for (int i = tid; i < nq; i += RASTER_THREADS)   // the records were read by the cull: keep them near
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(a.rec + 2 * (int64_t)s_queue[i]));
+                // ---- phase 2: rasterize the queued survivors, one splat per thread: every lane steps through ITS
+                //      splat's pixel rectangle (row-major), the trip count is the largest rectangle of the warp's 32
+                //      splats.  Accepted fragments go to the warp's own buffer (no atomics, no election: the fill
+                //      level is a warp-uniform register) and are inserted 32 at a time when it runs full ----
                 int wcount = 0;
-                {
-                    const int per = (nq + RASTER_THREADS / 32 - 1) / (RASTER_THREADS / 32);
-                    int whead = min(nq, warp * per);
-                    const int wend = min(nq, whead + per);
-                    const unsigned int lt_mask = (1u << lane) - 1u;
+                for (int ib = 0; ib < nq; ib += RASTER_THREADS) {
+                    const int i = ib + tid;
+                    const bool have = i < nq;
+                    const int sid = have ? s_queue[i] : 0;
                     float4 A = make_float4(0.f, 0.f, 0.f, 0.f), Bv = make_float4(0.f, 0.f, 0.f, 0.f);
                     float cut = 0.f;
-                    unsigned long long key = 0;
-                    int xl = 0, yl = 0, xl0 = 0, xl1 = 0, rem = 0;
-                    for (;;) {
-                        const unsigned need = __ballot_sync(FULL, rem == 0);
-                        const int avail = wend - whead;
-                        if (need && avail > 0) {
-                            const int r = __popc(need & lt_mask);
-                            if (rem == 0 && r < avail) {
-                                const int sid = s_queue[whead + r];
-                                const unsigned int rc = s_qrect[whead + r];
-                                A = __ldg(&a.rec[2 * (int64_t)sid]);
-                                Bv = __ldg(&a.rec[2 * (int64_t)sid + 1]);
-                                cut = (PER_POINT_CUTOFF && a.cutoff) ? __ldg(&a.cutoff[sid]) : a.cutoff_uniform;
-                                key = make_key(A.z + 0.0f, sid);
-                                xl0 = rc & 15;
-                                yl = (rc >> 4) & 15;
-                                xl1 = (rc >> 8) & 15;
-                                xl = xl0;
-                                rem = (xl1 - xl0 + 1) * ((int)((rc >> 12) & 15) - yl + 1);
-                            }
-                            whead += min(__popc(need), avail);
-                        }
-                        if (!__any_sync(FULL, rem != 0)) {
-                            if (whead >= wend) break;
-                            continue;
-                        }
-                        const bool active = rem != 0;
+                    if (have) {
+                        A = __ldg(&a.rec[2 * (int64_t)sid]);
+                        Bv = __ldg(&a.rec[2 * (int64_t)sid + 1]);
+                        cut = (PER_POINT_CUTOFF && a.cutoff) ? __ldg(&a.cutoff[sid]) : a.cutoff_uniform;
+                    }
+                    const unsigned long long key = make_key(A.z + 0.0f, sid);
+                    int x0 = tx0, x1 = tx0 - 1, y0 = ty0, y1 = ty0 - 1;
+                    if (have) {
+                        pixel_range(A.x, A.w, tx0, tx1, S, inv_S, pow2, half_S, x0, x1);
+                        pixel_range(A.y, Bv.x, ty0, ty1, S, inv_S, pow2, half_S, y0, y1);
+                    }
+                    const int w = max(x1 - x0 + 1, 0), h = max(y1 - y0 + 1, 0);
+                    const int c = w * h;
+                    const int Cm = __reduce_max_sync(FULL, c);
+                    int xl = (c > 0) ? x0 - tx0 : 0, yl = (c > 0) ? y0 - ty0 : 0;
+                    const int xl0 = xl, xl1 = (c > 0) ? x1 - tx0 : 0;
+                    for (int t = 0; t < Cm; ++t) {
+                        const bool active = t < c;
                         const int pixl = yl * RASTER_TILE + xl;
                         const unsigned long long kth = lds_u64_volatile(sa_kth + pixl * (KMAX * 8));
                         const float dx = lds_f32(sa_xf + xl * 4) - A.x;
@@ -584,20 +563,18 @@ raster_sliced_kernel(const __grid_constant__ RasterArgs a) {
                             }
                             if (ok) {
                                 if (STATS) st_acc++;
-                                const int pi = wcount + __popc(pm & lt_mask);
+                                const int pi = wcount + __popc(pm & ((1u << lane) - 1u));
                                 sts_u64(sa_wkey + pi * 8, key);
                                 sts_u16(sa_wpix + pi * 2, (unsigned short)pixl);
                             }
                             wcount += __popc(pm);
                         }
-                        // next pixel of this lane's rectangle
-                        if (active) {
-                            --rem;
+                        // next pixel of this lane's rectangle; lanes that are done stay on their last pixel
+                        if (t + 1 < c) {
                             if (++xl > xl1) {
                                 xl = xl0;
                                 ++yl;
                             }
-                            if (rem == 0) yl = 0, xl = 0;   // idle lanes point at a valid pixel
                         }
                     }
                 }
