@@ -120,7 +120,8 @@ def _run_case(dev, P0, N, S, K, seed, with_coarse_fine):
     contrib = (g[..., None, :3].double() * w[..., None])[valid]                        # (F,3)
     wantc = torch.zeros(P0, 3, dtype=torch.float64, device=dev)
     wantc.index_add_(0, (idx[valid] % P0), contrib)
-    torch.testing.assert_close(c.grad.double(), wantc, rtol=2e-4, atol=1e-9)
+    # (float atomics in arbitrary order: entries that are sums of cancelling terms need an absolute floor)
+    torch.testing.assert_close(c.grad.double(), wantc, rtol=2e-4, atol=1e-5 * wantc.abs().max().item())
 
 
 def test_c2_100k_8views_512_matches_reference_cuda(cuda_device):
