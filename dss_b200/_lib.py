@@ -10,7 +10,7 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libdss_b200.so")
+LIB_PATH = os.environ.get("DSS_B200_LIB") or os.path.join(_HERE, "lib", "libdss_b200.so")   # (override: A/B builds)
 
 DSS_OK = 0
 DSS_E_CAPACITY = -4

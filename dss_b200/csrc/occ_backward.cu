@@ -725,6 +725,7 @@ occ_tile_kernel(const __grid_constant__ OccTileArgs a) {
         else if (need <= 16) occ_item<4, 2, POW2, NCONS>(a, it, s_gm, s_gp, s_xf, s_yf, rec, warp, lane);
         else if (need <= 24) occ_item<4, 3, POW2, NCONS>(a, it, s_gm, s_gp, s_xf, s_yf, rec, warp, lane);
         else if (need <= 32) occ_item<4, 4, POW2, NCONS>(a, it, s_gm, s_gp, s_xf, s_yf, rec, warp, lane);
+        else if (need <= 40) occ_item<4, 5, POW2, NCONS>(a, it, s_gm, s_gp, s_xf, s_yf, rec, warp, lane);   // not 48: -17 % pairs
         else if (need <= 48) occ_item<8, 3, POW2, NCONS>(a, it, s_gm, s_gp, s_xf, s_yf, rec, warp, lane);
         else if (need <= 64) occ_item<8, 4, POW2, NCONS>(a, it, s_gm, s_gp, s_xf, s_yf, rec, warp, lane);
         else occ_item<16, 3, POW2, NCONS>(a, it, s_gm, s_gp, s_xf, s_yf, rec, warp, lane);   // need <= 96 (R_box <= 40)

@@ -344,8 +344,15 @@ __device__ __forceinline__ void sts_u16(uint32_t addr, unsigned short v) {
     asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
 }
 
+#ifndef DSS_RASTER_WPEND
+#define DSS_RASTER_WPEND 128
+#endif
+#ifndef DSS_RASTER_QFILL
+#define DSS_RASTER_QFILL 768
+#endif
 constexpr int RASTER_QCAP = 1024;
-constexpr int RASTER_WPEND = 256;   // accepted fragments a warp buffers before it inserts them
+constexpr int RASTER_WPEND = DSS_RASTER_WPEND;   // accepted fragments a warp buffers before it inserts them
+constexpr int RASTER_QFILL = DSS_RASTER_QFILL;   // survivors queued before a rasterization phase starts (<= QCAP - 256)
 
 // lock-free sorted insert of one key into a pixel's K slots (chain of atomicMin, see above)
 template <int KMAX>
@@ -516,7 +523,7 @@ raster_sliced_kernel(const __grid_constant__ RasterArgs a) {
             __syncthreads();
             const int nq = s_qcount;
             __syncthreads();   // everyone has read nq before the next chunk's appends can change it
-            if (more && nq <= RASTER_QCAP - RASTER_THREADS && base < end) continue;   // keep filling
+            if (more && nq <= RASTER_QFILL && base < end) continue;   // keep filling
             if (nq > 0) {
                 // ---- phase 2: rasterize the queued survivors, one splat per thread: every lane steps through ITS
                 //      splat's pixel rectangle (row-major), the trip count is the largest rectangle of the warp's 32

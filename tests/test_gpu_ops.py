@@ -216,6 +216,8 @@ def test_grid_insert_and_counting_sort(cuda_device):
 @pytest.mark.parametrize("S,P,rad_px,expect", [
     (96, 3000, (0.8, 4.0), "4 lanes/splat, table-driven rows (S not a power of two)"),
     (256, 6000, (2.0, 5.0), "8 lanes x 3 pairs"),
+    (256, 6000, (1.8, 4.2), "around the 4 lanes x 5 pairs mapping (33..40 columns)"),
+    (256, 6000, (2.2, 4.4), "around the 4 lanes x 5 pairs mapping (33..40 columns)"),
     (200, 5000, (4.0, 7.0), "8 lanes x 4 pairs, S not a power of two"),
     (256, 5000, (6.0, 9.0), "16 lanes x 3 pairs"),
     (256, 3000, (9.0, 13.0), "window larger than the staged box: direct gather"),
