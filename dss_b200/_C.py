@@ -12,7 +12,7 @@ import torch
 from . import _lib
 
 __all__ = ["splat_points", "_splat_points_naive", "_rasterize_coarse", "_rasterize_coarse_csr",
-           "_rasterize_fine", "_splat_points_occ_fast_cuda_backward", "_backward_zbuf"]
+           "_rasterize_fine", "_splat_points_occ_backward", "_splat_points_occ_fast_cuda_backward", "_backward_zbuf"]
 
 
 def _check_packed(points, ellipse_params, cutoff_thres, radii, first_idx, num_points):
@@ -141,6 +141,29 @@ def _rasterize_fine(points, ellipse_params, cutoff_thres, radii, bin_points, dep
     npts = torch.full((1,), P, dtype=torch.int64, device=points.device)
     return splat_points(points, ellipse_params, cutoff_thres, radii, fi, npts, depth_merging_thres, image_size,
                         points_per_pixel, bin_size, 0)
+
+
+def _splat_points_occ_backward(points, radii, grad_occ, cloud_to_packed_first_idx, num_points_per_cloud, radii_s,
+                               depth_merging_thres=0.05):
+    """``_C._splat_points_occ_backward`` (ext.cpp:10,16; rasterize_points.cu:673-821), the reference's SLOW occupancy
+    backward (rectangular window ``radii * radii_s``, every renderable point): -> ``(P,2)``.  ``depth_merging_thres`` is
+    accepted and unused, as in the reference kernel.  The training path uses the fast variant (rasterizer.py:816)."""
+    dev = _lib.require_cuda(points, radii, grad_occ, cloud_to_packed_first_idx, num_points_per_cloud)
+    _check_packed(points, None, None, radii, cloud_to_packed_first_idx, num_points_per_cloud)
+    if grad_occ.dim() != 3 or grad_occ.shape[1] != grad_occ.shape[2]:
+        raise RuntimeError("grad_occ must have shape (N, S, S)")
+    N, S, P = grad_occ.shape[0], grad_occ.shape[1], points.shape[0]
+    points = _lib.as_f32(points.detach(), "points")
+    radii = _lib.as_f32(radii.detach(), "radii")
+    grad_occ = _lib.as_f32(grad_occ.detach(), "grad_occ")
+    out = torch.empty((P, 2), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().dss_occ_backward_slow(
+            _lib.ctx(dev), _lib.ptr(points), _lib.ptr(radii), _lib.ptr(grad_occ), 1, 0,
+            _lib.ptr(cloud_to_packed_first_idx.contiguous()), _lib.ptr(num_points_per_cloud.contiguous()), N, P, S,
+            float(radii_s), _lib.ptr(out), _lib.stream_ptr(dev))
+    _lib.check(rc, "dss_occ_backward_slow")
+    return out
 
 
 def _splat_points_occ_fast_cuda_backward(points_sorted, radii_sorted, rs, grad_occ, num_points_per_cloud,

@@ -73,6 +73,8 @@ _SIGNATURES = {
     "dss_search_radius": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int64, C.c_float, vp, vp]),
     "dss_occ_backward": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int64,
                                    C.c_int, vp, vp]),
+    "dss_occ_backward_slow": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int64, C.c_int, C.c_float,
+                                        vp, vp]),
     "dss_zbuf_backward": (C.c_int, [vp, vp, vp, C.c_int64, C.c_int, vp, vp]),
     "dss_knn_points": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_float,
                                  vp, vp, vp]),

@@ -836,6 +836,72 @@ occ_generic_kernel(const float4 *__restrict__ rec, const uint8_t *__restrict__ v
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// "Slow" occupancy backward (RasterizePointsOccBackwardCudaKernel, DSS/csrc/rasterize_points.cu:673-760; disabled in
+// the reference by backward_occ_fast = True, rasterizer.py:816, kept for completeness): EVERY renderable point of the view
+// (z >= 0, |x|,|y| <= 1 -- not only the visible ones) gathers over the RECTANGLE |dx| <= rx*s, |dy| <= ry*s instead of
+// the disc; positive gradients only count inside the splat's own bbox ((rx*s)/s, (ry*s)/s as the reference writes it).
+// Same gather formulation as occ_generic_kernel: one warp per point, lanes stride over the window, no atomics.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(OCC_WARPS * 32)
+occ_slow_kernel(const float *__restrict__ points, const float *__restrict__ radii, float radii_s,
+                const float *__restrict__ grad, int pix_stride, int pix_offset, const int64_t *__restrict__ first_idx,
+                const int64_t *__restrict__ num_points, int S, float2 *__restrict__ grad_xy) {
+    const int n = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const ViewRange vr = view_range(first_idx, num_points, n, 0);
+    const bool pow2 = (S & (S - 1)) == 0;
+    const float inv_S = 1.0f / (float)S, half_S = 0.5f * (float)S;
+    const float *gview = grad + ((int64_t)n * S * S) * pix_stride + pix_offset;
+    constexpr unsigned FULL = 0xffffffffu;
+    for (int64_t i = (int64_t)blockIdx.x * OCC_WARPS + warp; i < vr.count; i += (int64_t)gridDim.x * OCC_WARPS) {
+        const int64_t p = vr.first + i;
+        const float px = points[p * 3], py = points[p * 3 + 1], pz = points[p * 3 + 2];
+        float gx = 0.f, gy = 0.f;
+        if (!(pz < 0.0f || fabsf(py) > 1.0f || fabsf(px) > 1.0f)) {            // rasterize_points.cu:719
+            const float rxs = radii[p * 2] * radii_s, rys = radii[p * 2 + 1] * radii_s;   // :725-726
+            const float rxb = rxs / radii_s, ryb = rys / radii_s;                            // :744
+            const float top = (float)(S - 1);
+            const int xi_lo = (int)fminf(fmaxf(floorf((px - rxs + 1.0f) * half_S - 0.5f) - 1.0f, 0.0f), top + 1.0f);
+            const int xi_hi = (int)fmaxf(fminf(ceilf((px + rxs + 1.0f) * half_S - 0.5f) + 1.0f, top), -1.0f);
+            const int yi_lo = (int)fminf(fmaxf(floorf((py - rys + 1.0f) * half_S - 0.5f) - 1.0f, 0.0f), top + 1.0f);
+            const int yi_hi = (int)fmaxf(fminf(ceilf((py + rys + 1.0f) * half_S - 0.5f) + 1.0f, top), -1.0f);
+            const int W = xi_hi - xi_lo + 1, H = yi_hi - yi_lo + 1;
+            if (W > 0 && H > 0) {
+                const int total = W * H;
+                int wy = lane / W, wx = lane - wy * W;
+                const int step_y = 32 / W, step_x = 32 - step_y * W;
+                for (int w = lane; w < total; w += 32) {
+                    const int xi = xi_lo + wx, yi = yi_lo + wy;
+                    const float g = __ldg(gview + ((int64_t)(S - 1 - yi) * S + (S - 1 - xi)) * pix_stride);
+                    if (g != 0.0f) {
+                        const float dx = pix_to_ndc_fast(xi, S, inv_S, pow2) - px, dy = pix_to_ndc_fast(yi, S, inv_S, pow2) - py;
+                        const bool in_rect = !(fabsf(dx) > rxs || fabsf(dy) > rys);                       // :728
+                        const bool outside_splat = (fabsf(dx) > rxb) || (fabsf(dy) > ryb);               // :744
+                        if (in_rect && !(g > 0.0f && outside_splat)) {
+                            const float den = eps_denom(dx * dx + dy * dy, 1e-10f);                       // :752-753
+                            gx += dx / den * g;
+                            gy += dy / den * g;
+                        }
+                    }
+                    wx += step_x;
+                    wy += step_y;
+                    if (wx >= W) {
+                        wx -= W;
+                        wy += 1;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            gx += __shfl_xor_sync(FULL, gx, d);
+            gy += __shfl_xor_sync(FULL, gy, d);
+        }
+        if (lane == 0) grad_xy[p] = make_float2(gx, gy);
+    }
+}
+
 // rs: (N,) search radii -- an INPUT when radii_s < 0 (the _C-level op passes them in), otherwise computed here as
 // radii_s * lower median of the visible radii and written to rs.  grad_xy (P,2) is fully written.
 int occ_backward(dss_ctx *ctx, const float4 *rec, const uint8_t *visible, float *rs, float radii_s,
@@ -1004,6 +1070,26 @@ int dss_search_radius(dss_ctx *ctx, const float *radii, const uint8_t *visible, 
     DSS_REQUIRE(rs && first_idx && num_points && (P == 0 || (radii && visible)), "null pointer");
     return dss::search_radius(ctx, nullptr, radii, visible, first_idx, num_points, N, P, radii_s, rs,
                               (cudaStream_t)stream);
+}
+
+int dss_occ_backward_slow(dss_ctx *ctx, const float *points, const float *radii, const float *grad_occ, int pix_stride,
+                          int pix_offset, const int64_t *first_idx, const int64_t *num_points, int N, int64_t P,
+                          int image_size, float radii_s, float *grad_xy, void *stream) {
+    using namespace dss;
+    DSS_REQUIRE(ctx != nullptr, "ctx is null");
+    DSS_REQUIRE(N >= 0 && P >= 0 && image_size > 0, "bad size");
+    DSS_REQUIRE(pix_stride >= 1 && pix_offset >= 0 && pix_offset < pix_stride, "bad pixel stride/offset");
+    DSS_REQUIRE(radii_s > 0.0f, "radii_s must be positive");
+    if (N == 0 || P == 0) return DSS_OK;
+    DSS_REQUIRE(points && radii && grad_occ && first_idx && num_points && grad_xy, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    DSS_CUDA_TRY(cudaMemsetAsync(grad_xy, 0, (size_t)P * 2 * sizeof(float), st));   // rows outside every view range
+    StageScope prof(ctx, ST_OCC_BWD, st);
+    dim3 grid(occ_nblocks(P, OCC_WARPS, ctx->sm_count, 16), N);
+    occ_slow_kernel<<<grid, OCC_WARPS * 32, 0, st>>>(points, radii, radii_s, grad_occ, pix_stride, pix_offset, first_idx,
+                                                     num_points, image_size, reinterpret_cast<float2 *>(grad_xy));
+    DSS_LAUNCH_CHECK(ctx);
+    return DSS_OK;
 }
 
 int dss_occ_backward(dss_ctx *ctx, const float *points, const float *radii, const uint8_t *visible,

@@ -159,6 +159,16 @@ DSS_API int dss_occ_backward(dss_ctx *ctx, const float *points, const float *rad
                      const int64_t *first_idx, const int64_t *num_points, int N, int64_t P,
                      int image_size, float *grad_xy, void *stream);
 
+/* The reference's "slow" occupancy backward, _C._splat_points_occ_backward (DSS/csrc/ext.cpp:10,16;
+ * rasterize_points.cu:673-821) -- disabled in the reference by backward_occ_fast = True (rasterizer.py:816), provided
+ * for completeness: every renderable point (z >= 0, |x|,|y| <= 1) of view n gathers
+ *   grad_xy[p] = sum over pixels with g != 0, |dx| <= rx*s, |dy| <= ry*s, not (g > 0 and outside the splat's bbox)
+ *                of (dx,dy) / eps_denom(dx^2 + dy^2, 1e-10) * g .
+ * grad_occ addressing as in dss_occ_backward.  grad_xy (P,2) fully written.  Deterministic (gather, no atomics). */
+DSS_API int dss_occ_backward_slow(dss_ctx *ctx, const float *points, const float *radii, const float *grad_occ,
+                                  int pix_stride, int pix_offset, const int64_t *first_idx, const int64_t *num_points,
+                                  int N, int64_t P, int image_size, float radii_s, float *grad_xy, void *stream);
+
 /* z_grad[idx_k] += grad_zbuf_k until the first idx < 0.  Replaces _C._backward_zbuf
  * (DSS/csrc/ext.cpp:17; rasterize_points.h:388-419; rasterize_points.cu:823-885).  z_grad (P,) in-place. */
 DSS_API int dss_zbuf_backward(dss_ctx *ctx, const int32_t *idx, const float *grad_zbuf, int64_t num_pixels,

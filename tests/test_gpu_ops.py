@@ -241,3 +241,29 @@ def test_occ_backward_window_variants(cuda_device, S, P, rad_px, expect):
         out = _C.occ_backward(*args).cpu().numpy()
         assert np.abs(out - g64).max() <= 2e-5 * scale + 1e-9, (expect, attempt, np.abs(out - g64).max() / scale)
         assert (out[vis == 0] == 0).all()
+
+
+@pytest.mark.parametrize("S,P,N,radii_s", [(96, 3000, 2, 2.0), (128, 5000, 3, 3.5)])
+def test_slow_occ_backward_matches_oracle_and_reference_cuda(cuda_device, S, P, N, radii_s):
+    """A17: the reference's slow occupancy backward (rasterize_points.cu:673-821; rectangular window, every renderable
+    point), disabled in the reference but part of its native surface: our gather vs the oracle's restatement and, when
+    the witness is built, vs the reference's own CUDA kernel (float atomics in arbitrary order there)."""
+    from dss_b200 import _C
+    pts, ell, cut, rad, first, num = random_screen_splats(P, N, S, seed=S + N)
+    rng = np.random.default_rng(S)
+    g = (rng.standard_normal((N, S, S)) * 1e-3).astype(np.float32)
+    g[rng.random((N, S, S)) < 0.3] = 0.0
+    d = cuda_device
+    out = _C._splat_points_occ_backward(_t(pts, d), _t(rad, d), _t(g, d), _t(first, d), _t(num, d), radii_s, 0.05)
+    want = oracle.occ_backward_slow(pts, rad, g, first, num, radii_s, cpu_twin=False)
+    scale = np.abs(want).max()
+    assert scale > 0
+    assert np.abs(out.cpu().numpy() - want).max() <= 1e-4 * scale
+    # points behind the camera or outside the image get nothing (rasterize_points.cu:719)
+    dead = (pts[:, 2] < 0) | (np.abs(pts[:, 0]) > 1) | (np.abs(pts[:, 1]) > 1)
+    assert dead.any() and (out.cpu().numpy()[dead] == 0).all()
+    from oracle import build_ref
+    ref = build_ref.ref_cuda()
+    if ref is not None:
+        r = ref.splat_points_occ_backward_cuda(_t(pts, d), _t(rad, d), _t(g, d), _t(first, d), _t(num, d), radii_s, 0.05)
+        assert (out - r).abs().max().item() <= 1e-4 * scale
