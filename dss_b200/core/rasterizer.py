@@ -190,13 +190,56 @@ class SurfaceSplatting(nn.Module):
             point_clouds = point_clouds.extend(cameras.R.shape[0])
         return point_clouds
 
+    def filter_renderable(self, point_clouds, point_clouds_filter=None, **kwargs):
+        """rasterizer.py:219-254 (+ :183-217, :148-181) with the reference's COMPACTION semantics: returns
+        ``(filtered_cloud, valid_mask)`` where the cloud holds, per view, only the points with
+        ``znear <= z_view <= zfar`` (and, with ``backface_culling``, a view-space normal with z < 0) and ``valid_mask``
+        (P,) marks them in the packed input.  The fused path does not need it (filtered points keep their slot with
+        depth -1, DESIGN.md hazard 12); ``forward(..., compact_filtered=True)`` renders the compacted cloud so that
+        ``idx`` indexes it exactly as in the reference."""
+        rs = kwargs.get("raster_settings", self.raster_settings)
+        cameras = self._cameras(kwargs)
+        if point_clouds.isempty():
+            return None, None
+        point_clouds = self._prepare_clouds(point_clouds, point_clouds_filter, cameras)
+        _, view = camera_matrices(cameras)
+        view = view.to(point_clouds.device)
+        znear = getattr(cameras, "znear", kwargs.get("znear", 1.0))
+        zfar = getattr(cameras, "zfar", kwargs.get("zfar", 100.0))
+        znear = float(torch.as_tensor(znear).reshape(-1)[0])
+        zfar = float(torch.as_tensor(zfar).reshape(-1)[0])
+        pts_l, nrm_l, feat_l, masks = [], [], [], []
+        normals, feats = point_clouds.normals_list(), point_clouds.features_list()
+        with torch.no_grad():
+            for n, pts in enumerate(point_clouds.points_list()):
+                zv = pts @ view[n][:3, 2] + view[n][3, 2]
+                m = (zv >= znear) & (zv <= zfar)
+                if rs.backface_culling and normals is not None:
+                    m = m & ((normals[n] @ view[n][:3, 2]) < 0)
+                masks.append(m)
+        for n, pts in enumerate(point_clouds.points_list()):
+            pts_l.append(pts[masks[n]])
+            if normals is not None:
+                nrm_l.append(normals[n][masks[n]])
+            if feats is not None:
+                feat_l.append(feats[n][masks[n]])
+        out = point_clouds.__class__(pts_l, nrm_l if normals is not None else None, feat_l if feats is not None else None)
+        return out, torch.cat(masks)
+
     def forward(self, point_clouds, point_clouds_filter=None, **kwargs):
         """-> (PointFragments, point_clouds[, per_point_info if verbose])  (rasterizer.py:584-664)."""
         rs = kwargs.get("raster_settings", self.raster_settings)
         cameras = self._cameras(kwargs)
         if point_clouds.isempty():
             return self._empty_fragments(cameras.R.shape[0], **kwargs), point_clouds
-        point_clouds = self._prepare_clouds(point_clouds, point_clouds_filter, cameras)
+        if kwargs.get("compact_filtered", False):
+            # the reference's index space: render the compacted clouds (the activation filter has been applied by
+            # filter_renderable already; the visibility written back refers to the compacted cloud, as in the reference)
+            point_clouds, _ = self.filter_renderable(point_clouds, point_clouds_filter, **kwargs)
+            point_clouds_filter_for_prepare = None
+        else:
+            point_clouds_filter_for_prepare = point_clouds_filter
+        point_clouds = self._prepare_clouds(point_clouds, point_clouds_filter_for_prepare, cameras)
         with torch.no_grad():
             info = self._get_per_point_info(point_clouds, **kwargs)
         pts_screen = self.transform(point_clouds, **kwargs)

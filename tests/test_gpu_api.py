@@ -140,3 +140,28 @@ def test_cpu_tensors_fail_loudly():
     with pytest.raises(RuntimeError):
         _C.splat_points(z, z, torch.ones(4), torch.ones(4, 2), torch.zeros(1, dtype=torch.int64),
                         torch.full((1,), 4, dtype=torch.int64), 0.05, 16, 5, 0, 0)
+
+
+def test_filter_renderable_compaction_matches_slot_semantics(cuda_device):
+    """SurfaceSplatting.filter_renderable returns the reference's compacted cloud (rasterizer.py:219-254);
+    forward(compact_filtered=True) renders it: same fragments as the default slot-keeping path up to the compaction map."""
+    dev = cuda_device
+    pts, nrm, col, cams, rast, renderer = _setup(dev, P0=6000, N=3, S=96)
+    rast.raster_settings.backface_culling = True
+    cloud = PointClouds3D([pts], normals=[nrm], features=[col])
+    filtered, mask = rast.filter_renderable(cloud, cameras=cams)
+    N = len(cams)
+    assert mask.shape == (N * 6000,) and len(filtered) == N
+    num = filtered.num_points_per_cloud()
+    assert torch.equal(num, mask.view(N, -1).sum(1))
+    assert 0.3 < mask.float().mean().item() < 0.7
+    frag_slot, _ = rast(cloud, cameras=cams)
+    frag_comp, cloud_comp = rast(cloud, cameras=cams, compact_filtered=True)
+    assert int(cloud_comp.num_points_per_cloud().sum()) == int(mask.sum())
+    remap = (torch.cumsum(mask.long(), 0) - 1).to(torch.int32)
+    mapped = torch.where(frag_slot.idx >= 0, remap[frag_slot.idx.clamp(min=0).long()], torch.full_like(frag_slot.idx, -1))
+    # the float64-free torch mask and the kernel's fp32 mask agree except for normals within rounding of edge-on
+    same = (mapped == frag_comp.idx).all(-1)
+    assert same.float().mean().item() > 0.999
+    assert torch.equal(frag_slot.zbuf[same], frag_comp.zbuf[same])
+    rast.raster_settings.backface_culling = False
