@@ -155,8 +155,11 @@ def test_filter_renderable_compaction_matches_slot_semantics(cuda_device):
     num = filtered.num_points_per_cloud()
     assert torch.equal(num, mask.view(N, -1).sum(1))
     assert 0.3 < mask.float().mean().item() < 0.7
-    frag_slot, _ = rast(cloud, cameras=cams)
-    frag_comp, cloud_comp = rast(cloud, cameras=cams, compact_filtered=True)
+    # same splat size in both modes (left to itself the compact mode sizes the splats from each view's FILTERED cloud,
+    # like the reference, the slot mode from the whole cloud: DESIGN.md hazard 12)
+    h = torch.full((N,), 3e-4, device=dev)
+    frag_slot, _ = rast(cloud, cameras=cams, Vrk_h=h)
+    frag_comp, cloud_comp = rast(cloud, cameras=cams, compact_filtered=True, Vrk_h=h)
     assert int(cloud_comp.num_points_per_cloud().sum()) == int(mask.sum())
     remap = (torch.cumsum(mask.long(), 0) - 1).to(torch.int32)
     mapped = torch.where(frag_slot.idx >= 0, remap[frag_slot.idx.clamp(min=0).long()], torch.full_like(frag_slot.idx, -1))
