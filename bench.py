@@ -43,6 +43,10 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-sample-points", type=int, default=20000)
+    ap.add_argument("--colours", default="point", choices=["point", "view", "shaded"],
+                    help="point: one RGB per point shared by the views (default, the BASELINE line); view: per-(view,point) "
+                         "colours (V*P0,3) as the reference holds them after shading; shaded: per-point albedo + fused "
+                         "shading (one directional light), gradients to albedo, normals and positions")
     return ap.parse_args()
 
 
@@ -286,7 +290,7 @@ def run_ours(a):
     # colours: one RGB per POINT, shared by the views of the step (the quantity an inverse-rendering step optimises
     # and the one exchange step reduces); per-(view,point) colours -- the layout the reference holds on the device after
     # shading -- take the same path with a (V*P0,3) tensor (tests/test_gpu_render.py).
-    colours_h = col.contiguous().pin_memory()
+    colours_h = (col.repeat(V, 1) if a.colours == "view" else col).contiguous().pin_memory()
     grad_h = (torch.randn(V, S, S, 4, generator=g) * 1e-3).pin_memory()        # dense, like the IoU term
     pts_h, nrm_h = pts.pin_memory(), nrm.pin_memory()
     h_h = torch.full((V,), 5e-5).pin_memory()   # clamp floor of the 6-NN rule at this density (rasterizer.py:326)
@@ -296,10 +300,18 @@ def run_ours(a):
     nrm_d, col_d = nrm_h.to(dev), colours_h.to(dev).requires_grad_(True)
     proj_d, view_d, h_d, grad_d = proj_h.to(dev), view_h.to(dev), h_h.to(dev), grad_h.to(dev)
 
+    shading = None
+    if a.colours == "shaded":
+        from dss_b200.core.lighting import DirectionalLights
+        from dss_b200.ops import make_shading
+        shading = make_shading(DirectionalLights(direction=(((0.3, 1.0, 0.4),),), device=dev), view_d, shininess=64.0)
+        nrm_d.requires_grad_(True)
+
     def step_resident():
         pts_d.grad = None
         col_d.grad = None
-        out = render_points(pts_d, nrm_d, col_d, proj_d, view_d, h_d, prm, grad_sync=sync)
+        nrm_d.grad = None
+        out = render_points(pts_d, nrm_d, col_d, proj_d, view_d, h_d, prm, grad_sync=sync, shading=shading)
         out.image.backward(grad_d)            # gradients come back already summed over the ranks
         return out
 
@@ -353,7 +365,7 @@ def run_ours(a):
     if not a.no_e2e:
         img_h = torch.empty(V, S, S, 4).pin_memory()
         gpts_h = torch.empty(P0, 3).pin_memory()
-        gcol_h = torch.empty(P0, 3).pin_memory()
+        gcol_h = torch.empty_like(colours_h).pin_memory()
         # host-side inputs of a step: the cloud (positions, normals, per-point colours), this rank's cameras and the
         # image gradient.  Colours go up once per POINT (P0,3): the reference only materialises per-(view,point)
         # colours on the device (after shading), it never uploads them.
@@ -403,7 +415,8 @@ def run_ours(a):
             mark("compute_begin", main)
             p = d[0].detach().requires_grad_(True)
             c = d[2].detach().requires_grad_(True)
-            out = render_points(p, d[1], c, d[3], d[4], d[5], prm, grad_sync=sync)
+            nn_ = d[1].detach().requires_grad_(True) if shading is not None else d[1]
+            out = render_points(p, nn_, c, d[3], d[4], d[5], prm, grad_sync=sync, shading=shading)
             mark("forward_end", main)
             out.image.backward(d[6])
             gp, gc = p.grad, c.grad        # summed over all ranks' views: the reduced gradients go back to the host
@@ -525,7 +538,10 @@ def run_ours(a):
                    "overlapped with the occupancy gather) and of d position (behind the chain kernel)" % V
                    if world > 1 else "single GPU",
                    "l2": "per-step inputs %.0f MB + %.0f MB of splat records exceed the 126 MB L2" % (work_mb, V * P0 * 32 / 1e6),
-                   "colours": "per point (P0,3), shared by the views",
+                   "colours": {"point": "per point (P0,3), shared by the views",
+                               "view": "per (view, point) (V*P0,3), the layout the reference holds after shading",
+                               "shaded": "per-point albedo (P0,3) + fused shading (1 directional light): gradients to "
+                                         "albedo, normals, positions"}[a.colours],
                    "settings": "configs/dss.yml:14-22 (cutoff 1, merge 0.05, K=5, radii_s 5, clip 0.05, sigma 1)"},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         "allreduce": allreduce,

@@ -416,6 +416,7 @@ raster_sliced_kernel(const __grid_constant__ RasterArgs a) {
     __shared__ unsigned short s_pend_pix[RASTER_THREADS / 32][RASTER_WPEND];       //           waiting for insertion
     __shared__ float s_xf[RASTER_TILE], s_yf[RASTER_TILE];   // exact pixel centres of the tile
     __shared__ unsigned int s_blk[16];
+    __shared__ unsigned int s_wblk[RASTER_THREADS / 32][4];   // per warp: K-th depth maxima of its four 4x2-pixel groups
     __shared__ int s_qcount;
     __shared__ unsigned int s_tilemax;
 
@@ -463,6 +464,7 @@ raster_sliced_kernel(const __grid_constant__ RasterArgs a) {
         // The tile's list is ordered by depth slice: walk it front to back in chunks of 256 entries.  Every entry at
         // or behind position `base` has z >= slice_bound(slice of base): stop as soon as that cannot enter any list.
         int base = beg, s_cur = 0;
+        int nq_acc = 0;   // survivors queued since the last rasterization phase (uniform)
         // software pipeline of the list walk: ids are fetched two chunks ahead, the (gathered) records one chunk ahead,
         // so that the dependent id -> record loads of a chunk are in flight while the previous chunk is rasterized
         int id0 = (beg + tid < end) ? list_id(beg + tid) : -1;
@@ -475,6 +477,7 @@ raster_sliced_kernel(const __grid_constant__ RasterArgs a) {
         }
         while (true) {
             bool more = base < end;
+            bool chunk_survive = false;
             if (more && !overflow) {
                 while (s_cur + 1 < NS && a.tile_offsets[tb + s_cur + 1] <= base) ++s_cur;
                 if (s_cur > 0 && __float_as_uint(slice_bound(sm, s_cur)) > s_tilemax) {
@@ -518,11 +521,13 @@ raster_sliced_kernel(const __grid_constant__ RasterArgs a) {
                     s_queue[wbase + __popc(m & ((1u << lane) - 1u))] = id;
                     if (STATS) st_surv++;
                 }
+                chunk_survive = survive;
                 base += RASTER_THREADS;
             }
-            __syncthreads();
-            const int nq = s_qcount;
-            __syncthreads();   // everyone has read nq before the next chunk's appends can change it
+            // one barrier gives every thread the number of survivors appended by this chunk (the queue slots themselves
+            // come from s_qcount's atomics, which the next chunk may already be using)
+            nq_acc += __syncthreads_count(chunk_survive);
+            const int nq = nq_acc;
             if (more && nq <= RASTER_QFILL && base < end) continue;   // keep filling
             if (nq > 0) {
                 // ---- phase 2: rasterize the queued survivors, one splat per thread: every lane steps through ITS
@@ -587,24 +592,30 @@ raster_sliced_kernel(const __grid_constant__ RasterArgs a) {
                 }
                 pend_flush<KMAX>(s_keys, wkey, wpix, wcount, lane);
                 __syncthreads();
-                // ---- phase 3: refresh the block / tile thresholds (K-th depth, pixels outside the image never block) ----
-                if (tid < 16) s_blk[tid] = 0;
-                if (tid == 0) s_qcount = 0;
-                __syncthreads();
+                // ---- phase 3: refresh the block / tile thresholds (K-th depth, pixels outside the image never block).
+                //      A warp covers two pixel rows: the 8 lanes of a 4-pixel x 2-row group reduce among themselves,
+                //      the two warps of a block row are combined after one barrier (no atomics, nothing to zero) ----
                 {
                     const int pxl = tid & (RASTER_TILE - 1), pyl = tid >> 4;
                     const bool in_img = (tx0 + pxl < S) && (ty0 + pyl < S);
                     const unsigned int kz = in_img ? (unsigned int)(s_keys[tid * KMAX + KMAX - 1] >> 32) : 0u;
-                    atomicMax(&s_blk[(pyl >> 2) * 4 + (pxl >> 2)], kz);
+                    const unsigned int gmask = 0x000f000fu << (4 * ((lane & 15) >> 2));
+                    const unsigned int gmax = __reduce_max_sync(gmask, kz);
+                    if ((lane & 19) == 0) s_wblk[warp][lane >> 2] = gmax;   // lanes 0, 4, 8, 12
+                    if (tid == 0) s_qcount = 0;
                 }
                 __syncthreads();
-                if (tid == 0) {
+                if (tid < 16) s_blk[tid] = max(s_wblk[2 * (tid >> 2)][tid & 3], s_wblk[2 * (tid >> 2) + 1][tid & 3]);
+                if (tid == 32) {
                     unsigned int mx = 0;
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) mx = max(mx, s_blk[i]);
+                    for (int i = 0; i < RASTER_THREADS / 32; ++i)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) mx = max(mx, s_wblk[i][c]);
                     s_tilemax = mx;
                 }
                 __syncthreads();
+                nq_acc = 0;
                 if (STATS && tid == 0) st_visit++;
             }
             if (!more || base >= end) break;
