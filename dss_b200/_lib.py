@@ -45,6 +45,7 @@ class RenderArgs(C.Structure):
         ("reserved0", C.c_int32),
         ("albedo", vp), ("lights", vp), ("ambient", vp), ("cam_centres", vp), ("shaded", vp),
         ("grad_albedo", vp), ("grad_normals_world", vp), ("grad_points_shading", vp),
+        ("cell_counts", vp),
     ]
 
 

@@ -91,6 +91,9 @@ struct RasterArgs {
     int64_t colour_P0;     // > 0: colour row of packed splat id in view n is id - n * colour_P0
     float *image;          // (N,S,S,4)
     float *weights;        // (N,S,S,K)
+    int32_t *cell_counts;  // optional (N*OB*OB*1024,), zeroed by the caller, OB = ceil(S/32): the blend epilogue counts every
+                           // visible splat once in the 32x32-tile / pixel cell of its centre (the count pass of the occupancy
+                           // backward's binning, fused); needs `visible` 4-byte aligned with capacity rounded up to 4
     uint8_t *visible;      // (P,) must be zeroed by the caller
     int64_t visible_count; // P (to re-zero `visible` when a pass has to be repeated)
     int force_pixel_parallel;  // testing: use the pixel-parallel kernel even for K <= 8
@@ -109,9 +112,12 @@ int search_radius(dss_ctx *ctx, const float4 *rec, const float *radii, const uin
                   const int64_t *first_idx, const int64_t *num_points, int N, int64_t P0, float radii_s,
                   float *rs, cudaStream_t st);
 // rs is an input when radii_s < 0, otherwise rs[n] = radii_s * lower median of the visible radii is computed here
+// cell_counts (optional): per-cell counts of the visible splats produced by the forward (RasterArgs::cell_counts); when
+// given and the cell-level binning is in use, the counting pass is replaced by a copy of these counts
 int occ_backward(dss_ctx *ctx, const float4 *rec, const uint8_t *visible, float *rs, float radii_s,
                  const float *grad_occ, int pix_stride, int pix_offset, const int64_t *first_idx,
-                 const int64_t *num_points, int N, int64_t P0, int S, float *grad_xy, cudaStream_t st);
+                 const int64_t *num_points, int N, int64_t P0, int S, float *grad_xy, const int32_t *cell_counts,
+                 cudaStream_t st);
 int zbuf_backward(dss_ctx *ctx, const int32_t *idx, const float *grad_zbuf, int64_t num_pixels, int K,
                   float *z_grad, int z_stride, cudaStream_t st);
 // colour_P0 > 0: grad_colours is (P0,3) shared by the views (pixels_per_view = S*S locates a pixel's view)

@@ -906,7 +906,8 @@ occ_slow_kernel(const float *__restrict__ points, const float *__restrict__ radi
 // radii_s * lower median of the visible radii and written to rs.  grad_xy (P,2) is fully written.
 int occ_backward(dss_ctx *ctx, const float4 *rec, const uint8_t *visible, float *rs, float radii_s,
                  const float *grad_occ, int pix_stride, int pix_offset, const int64_t *first_idx,
-                 const int64_t *num_points, int N, int64_t P0, int S, float *grad_xy, cudaStream_t st) {
+                 const int64_t *num_points, int N, int64_t P0, int S, float *grad_xy, const int32_t *cell_counts,
+                 cudaStream_t st) {
     if (N <= 0 || P0 <= 0) return DSS_OK;
     const int OB = (S + OCC_TILE - 1) / OCC_TILE;
     const int64_t nt = (int64_t)N * OB * OB;
@@ -965,9 +966,15 @@ int occ_backward(dss_ctx *ctx, const float4 *rec, const uint8_t *visible, float 
                 DSS_LAUNCH_CHECK(ctx);
             } else {
                 dim3 bgrid(occ_nblocks(P0, 256 * 4, ctx->sm_count, 8), N);
-                occ_cellbin_kernel<0><<<bgrid, 256, 0, st>>>(rec, visible, first_idx, num_points, P0, S, OB, counts, nullptr,
-                                                             nullptr, nullptr);
-                DSS_LAUNCH_CHECK(ctx);
+                if (cell_counts) {
+                    // the forward's blend epilogue has counted already (one count per visible splat, same cells): take a
+                    // copy -- pass 1 counts the working copy back down to zero, the caller's tensor stays intact
+                    DSS_CUDA_TRY(cudaMemcpyAsync(counts, cell_counts, (size_t)nc * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+                } else {
+                    occ_cellbin_kernel<0><<<bgrid, 256, 0, st>>>(rec, visible, first_idx, num_points, P0, S, OB, counts, nullptr,
+                                                                 nullptr, nullptr);
+                    DSS_LAUNCH_CHECK(ctx);
+                }
                 if ((rc = exclusive_scan_i32(ctx, counts, offsets, nc + 1, st))) return rc;
                 occ_cellbin_kernel<1><<<bgrid, 256, 0, st>>>(rec, visible, first_idx, num_points, P0, S, OB, counts, offsets,
                                                              crec, cids);
@@ -1108,7 +1115,7 @@ int dss_occ_backward(dss_ctx *ctx, const float *points, const float *radii, cons
     if ((rc = ctx_get(ctx, BUF_RECORDS, (size_t)(2 * P), &rec))) return rc;
     if ((rc = pack_records(ctx, points, radii, nullptr, P, rec, st))) return rc;
     return occ_backward(ctx, rec, visible, const_cast<float *>(rs), -1.0f, grad_occ, pix_stride, pix_offset, first_idx,
-                        num_points, N, P, image_size, grad_xy, st);
+                        num_points, N, P, image_size, grad_xy, nullptr, st);
 }
 
 }  // extern "C"

@@ -214,7 +214,7 @@ __device__ __forceinline__ void raster_epilogue(const RasterArgs &a, const unsig
     const int64_t pix = ((int64_t)n * S + (S - 1 - yi)) * S + (S - 1 - xi);
     const float xf = pix_to_ndc_fast(xi, S, inv_S, pow2);
     const float yf = pix_to_ndc_fast(yi, S, inv_S, pow2);
-    float fz[KMAX], fq[KMAX];
+    float fz[KMAX], fq[KMAX], fcx[KMAX], fcy[KMAX];
     int fid[KMAX];
     bool emit[KMAX];
     bool open = beg < end;
@@ -223,6 +223,7 @@ __device__ __forceinline__ void raster_epilogue(const RasterArgs &a, const unsig
     for (int k = 0; k < KMAX; ++k) {
         fz[k] = -1.0f;
         fq[k] = -1.0f;
+        fcx[k] = fcy[k] = 0.0f;
         fid[k] = -1;
         emit[k] = false;
         if (open && k < K) {
@@ -241,6 +242,8 @@ __device__ __forceinline__ void raster_epilogue(const RasterArgs &a, const unsig
                     const float dx = xf - A.x, dy = yf - A.y;
                     fz[k] = z;
                     fid[k] = id;
+                    fcx[k] = A.x;
+                    fcy[k] = A.y;
                     fq[k] = Bv.y * dx * dx + Bv.z * dx * dy + Bv.w * dy * dy;
                     emit[k] = true;
                 }
@@ -272,7 +275,21 @@ __device__ __forceinline__ void raster_epilogue(const RasterArgs &a, const unsig
                 g += w[k] * __ldg(c + 1);
                 b += w[k] * __ldg(c + 2);
                 wsum += w[k];
-                if (a.visible) a.visible[id] = 1;
+                if (a.cell_counts) {
+                    // visibility byte + (first setter only) one count in the backward binning's cell of the splat's
+                    // centre pixel: the backward's counting pass over all P splats disappears
+                    unsigned int *word = reinterpret_cast<unsigned int *>(a.visible) + (id >> 2);
+                    const unsigned int bit = 1u << ((id & 3) * 8);
+                    if (!(*reinterpret_cast<volatile unsigned int *>(word) & bit) && !(atomicOr(word, bit) & bit)) {
+                        const int cx = min(max((int)floorf((fcx[k] + 1.0f) * (0.5f * (float)S)), 0), S - 1);
+                        const int cy = min(max((int)floorf((fcy[k] + 1.0f) * (0.5f * (float)S)), 0), S - 1);
+                        const int OB = (S + 31) >> 5;
+                        const int64_t cell = (((int64_t)n * OB + (cy >> 5)) * OB + (cx >> 5)) * 1024 + (cy & 31) * 32 + (cx & 31);
+                        atomicAdd(&a.cell_counts[cell], 1);
+                    }
+                } else if (a.visible) {
+                    a.visible[id] = 1;
+                }
             }
         }
         const float inv = 1.0f / fmaxf(wsum, 1e-4f);

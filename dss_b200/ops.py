@@ -151,7 +151,11 @@ class _RenderFunction(torch.autograd.Function):
         image = torch.empty((N, S, S, 4), **f32)
         idx = torch.empty((N, S, S, K), dtype=torch.int32, device=dev)
         weights = torch.empty((N, S, S, K), **f32)
-        visible = torch.empty((P,), dtype=torch.uint8, device=dev)
+        # (capacity rounded up to 4 bytes: the blend epilogue sets the bytes with word atomics when it also counts the
+        #  visible splats per backward-binning cell, see dss_render_args.cell_counts)
+        visible = torch.empty(((P + 3) // 4 * 4,), dtype=torch.uint8, device=dev)[:P]
+        OB = (S + 31) // 32
+        cell_counts = torch.empty((N * OB * OB * 1024,), dtype=torch.int32, device=dev) if K <= 8 else None
         zbuf = torch.empty((N, S, S, K), **f32) if want_frags else None
         qvalue = torch.empty((N, S, S, K), **f32) if want_frags else None
         fi = first_idx.contiguous() if first_idx is not None else None
@@ -166,6 +170,7 @@ class _RenderFunction(torch.autograd.Function):
             a.shaded = _lib.ptr(shaded)
         a.records, a.scaler, a.image, a.idx = _lib.ptr(records), _lib.ptr(scaler), _lib.ptr(image), _lib.ptr(idx)
         a.weights, a.visible, a.zbuf, a.qvalue = _lib.ptr(weights), _lib.ptr(visible), _lib.ptr(zbuf), _lib.ptr(qvalue)
+        a.cell_counts = _lib.ptr(cell_counts)
         with torch.cuda.device(dev):
             rc = _lib.load().dss_render_forward(_lib.ctx(dev), C.byref(a), _lib.stream_ptr(dev))
         _lib.check(rc, "dss_render_forward")
@@ -174,6 +179,7 @@ class _RenderFunction(torch.autograd.Function):
         ctx.set_materialize_grads(False)
         ctx.save_for_backward(points_c, proj_c, view_c, records, idx, weights, visible, fi, npts)
         ctx.shading = (shading, normals_c, colours_c) if shading is not None else None
+        ctx.cell_counts = cell_counts
         ctx.meta = (shared, prm, N, P0, P, want_frags, shared_col, grad_sync)
         outs = (image, idx, weights, visible, records, scaler)
         if want_frags:
@@ -203,6 +209,7 @@ class _RenderFunction(torch.autograd.Function):
         a = _lib.RenderArgs()
         _fill_common(a, points_c, None, None, proj_c, view_c, None, fi, npts, shared, N, P0, P, prm)
         a.records, a.idx, a.weights, a.visible = _lib.ptr(records), _lib.ptr(idx), _lib.ptr(weights), _lib.ptr(visible)
+        a.cell_counts = _lib.ptr(ctx.cell_counts)
         a.shared_colours = int(shared_col)
         a.grad_image, a.grad_zbuf = _lib.ptr(grad_image), _lib.ptr(grad_zbuf)
         a.grad_colours, a.grad_points_world = _lib.ptr(grad_colours), _lib.ptr(grad_points)

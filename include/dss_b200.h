@@ -266,6 +266,11 @@ typedef struct dss_render_args {
     float *grad_normals_world;     /* (P0,3) summed over views                                     */
     float *grad_points_shading;    /* (P0,3) position gradient through the shading; dss_render_backward adds it to
                                       grad_points_world when it ran the colour half itself (grad_colours != NULL) */
+    /* optional (n_views * OB * OB * 1024,) int32, OB = ceil(S / 32): written by the forward (one count per visible splat in
+     * the cell -- pixel of a 32x32 tile -- of its centre; `visible` must then be 4-byte aligned with its capacity rounded
+     * up to a multiple of 4), read by the backward, whose binning then skips its counting pass over all P splats.  Give
+     * the same tensor to both calls or NULL to both. */
+    int32_t *cell_counts;
 } dss_render_args;
 #define DSS_MAX_LIGHTS 8
 
