@@ -81,9 +81,12 @@ template <bool POW2>
 __device__ __forceinline__ void bin_range(float p0, float p1, const EdgeCtx &e, int &lo, int &hi) {
     const int B = e.B;
     const float scale = (float)e.S / (2.0f * (float)e.bin);
-    // estimates (may be off by one or two; NaN/inf handled by the clamps and the exact fix-up)
-    float e0 = floorf((p0 + 1.0f) * scale) - 1.0f;
-    float e1 = floorf((p1 + 1.0f) * scale) + 1.0f;
+    // estimates: the bin that contains the end point (exact unless the point sits within rounding of an edge; NaN/inf are
+    // handled by the clamps).  The fix-up loops below correct any start in either direction, so the estimate only sets
+    // their trip count: two predicate evaluations per bound from here, three from the "one bin outside" start used before
+    // (the edge arithmetic was 56 % of bin_count_kernel's instructions, profiles/r02_ncu_bin_count_before.txt)
+    float e0 = floorf((p0 + 1.0f) * scale);
+    float e1 = floorf((p1 + 1.0f) * scale);
     lo = (e0 >= 0.0f) ? ((e0 < (float)B) ? (int)e0 : B) : 0;          // NaN -> 0
     hi = (e1 >= 0.0f) ? ((e1 < (float)B) ? (int)e1 : B - 1) : -1;    // NaN -> -1
     if (hi > B - 1) hi = B - 1;
