@@ -489,22 +489,35 @@ __global__ void __launch_bounds__(256) chain_kernel(const __grid_constant__ Chai
              i += (int64_t)gridDim.x * blockDim.x) {
             const float p0 = a.pts[i * 3], p1 = a.pts[i * 3 + 1], p2 = a.pts[i * 3 + 2];
             float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
-            for (int n = 0; n < a.N; ++n) {
-                const int64_t s = (int64_t)n * a.P0 + i;
-                const float2 g = a.gxy[s];
-                float gx = g.x, gy = g.y, gz = a.gz ? a.gz[s] : 0.0f;
-                clip_grad(a.clip, gx, gy, gz);
-                if (a.grad_ndc) {
-                    a.grad_ndc[s * 3 + 0] = gx;
-                    a.grad_ndc[s * 3 + 1] = gy;
-                    a.grad_ndc[s * 3 + 2] = gz;
+            // views in batches of four: the (independent) gradient loads of a batch are issued together
+            for (int n0 = 0; n0 < a.N; n0 += 4) {
+                float2 g4[4];
+                float gz4[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int64_t s = (int64_t)(n0 + j) * a.P0 + i;
+                    g4[j] = (n0 + j < a.N) ? a.gxy[s] : make_float2(0.f, 0.f);
+                    gz4[j] = (a.gz && n0 + j < a.N) ? a.gz[s] : 0.0f;
                 }
-                if (gx != 0.0f || gy != 0.0f || gz != 0.0f) {
-                    float w0, w1, w2;
-                    chain_one(sMat + n * 32, sMat + n * 32 + 16, p0, p1, p2, gx, gy, gz, w0, w1, w2);
-                    acc0 += w0;
-                    acc1 += w1;
-                    acc2 += w2;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int n = n0 + j;
+                    if (n >= a.N) break;
+                    const int64_t s = (int64_t)n * a.P0 + i;
+                    float gx = g4[j].x, gy = g4[j].y, gz = gz4[j];
+                    clip_grad(a.clip, gx, gy, gz);
+                    if (a.grad_ndc) {
+                        a.grad_ndc[s * 3 + 0] = gx;
+                        a.grad_ndc[s * 3 + 1] = gy;
+                        a.grad_ndc[s * 3 + 2] = gz;
+                    }
+                    if (gx != 0.0f || gy != 0.0f || gz != 0.0f) {
+                        float w0, w1, w2;
+                        chain_one(sMat + n * 32, sMat + n * 32 + 16, p0, p1, p2, gx, gy, gz, w0, w1, w2);
+                        acc0 += w0;
+                        acc1 += w1;
+                        acc2 += w2;
+                    }
                 }
             }
             if (a.gshade) {
