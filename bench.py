@@ -42,6 +42,7 @@ def parse_args():
     ap.add_argument("--k", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays (N = 1)")
     ap.add_argument("--cpu-sample-points", type=int, default=20000)
     ap.add_argument("--colours", default="point", choices=["point", "view", "shaded"],
                     help="point: one RGB per point shared by the views (default, the BASELINE line); view: per-(view,point) "
@@ -329,18 +330,52 @@ def run_ours(a):
     if sync is not None:
         sync.timings_ms()
         sync.reset_counters()
+    # per-stage device times (the library's own CUDA-event brackets) from an eager pass of a few steps ...
     _lib.profile_reset(dev)
     _lib.profile_enable(True, dev)
     launches0 = _lib.launch_count(dev)
+    n_prof = min(a.steps, 20)
+    for _ in range(n_prof):
+        step_resident()
+    sync_all()
+    launches_per_step = (_lib.launch_count(dev) - launches0) / n_prof
+    stages = {k: (v[0] * a.steps / n_prof, v[1]) for k, v in _lib.profile_read(dev).items()}   # scaled to `steps`
+    _lib.profile_enable(False, dev)
+    if sync is not None:
+        sync.timings_ms()
+        sync.reset_counters()
+    # ... and the timed region: K steps, replayed from ONE captured CUDA graph of the whole step on a single GPU (the
+    # library neither synchronises nor allocates in steady state: dss_b200/graph.py), launched eagerly otherwise
+    graphed = None
+    if world == 1 and not a.no_graph:
+        try:
+            from dss_b200.graph import GraphedRenderStep
+            graphed = GraphedRenderStep(pts_d, nrm_d, col_d, proj_d, view_d, h_d, prm, grad_d, shading=shading)
+            for _ in range(3):
+                graphed.replay()
+        except Exception as e:   # pragma: no cover
+            print("CUDA-graph capture failed, timing the eager loop: %r" % (e,), file=sys.stderr)
+            graphed = None
+    sync_all()
     sampler = ClockSampler(local)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(a.steps):
-        step_resident()
+        if graphed is not None:
+            graphed.replay()
+        else:
+            step_resident()
     e1.record()
     sync_all()
     clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    launches = launches_per_step * a.steps      # kernels executed in the timed region (replayed, not re-launched, under a graph)
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * V * P0 * a.steps / (ms_max * 1e-3) / 1e6
     allreduce = None
     if sync is not None:
         ar_ms = sync.timings_ms() / a.steps
@@ -542,6 +577,7 @@ def run_ours(a):
                                "view": "per (view, point) (V*P0,3), the layout the reference holds after shading",
                                "shaded": "per-point albedo (P0,3) + fused shading (1 directional light): gradients to "
                                          "albedo, normals, positions"}[a.colours],
+                   "launch": "one CUDA graph per step (captured fwd+bwd, dss_b200.graph)" if graphed is not None else "eager",
                    "settings": "configs/dss.yml:14-22 (cutoff 1, merge 0.05, K=5, radii_s 5, clip 0.05, sigma 1)"},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         "allreduce": allreduce,

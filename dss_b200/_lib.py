@@ -63,6 +63,7 @@ _SIGNATURES = {
     "dss_profile_read": (C.c_int, [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "dss_debug_raster_stats": (C.c_int, [vp, C.c_int, C.POINTER(C.c_uint64)]),
     "dss_debug_limit_tile_capacity": (C.c_int, [vp, C.c_int64]),
+    "dss_debug_tile_total": (C.c_int64, [vp]),
     "dss_exclusive_scan_i32": (C.c_int, [vp, vp, vp, C.c_int64, vp]),
     "dss_grid_insert_points_2d": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
     "dss_grid_counting_sort_2d": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),

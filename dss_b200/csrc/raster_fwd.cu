@@ -828,6 +828,11 @@ int dss_debug_raster_stats(dss_ctx *ctx, int enable, uint64_t out[8]) {
     return DSS_OK;
 }
 
+int64_t dss_debug_tile_total(const dss_ctx *ctx) {
+    // the tile-list size the device published last (mapped pinned word, read without synchronising)
+    return ctx ? (int64_t)(*reinterpret_cast<volatile int32_t *>(ctx->h_pinned)) : 0;
+}
+
 int dss_debug_limit_tile_capacity(dss_ctx *ctx, int64_t max_entries) {
     DSS_REQUIRE(ctx != nullptr, "ctx is null");
     DSS_REQUIRE(max_entries >= 0 && max_entries <= (int64_t)INT32_MAX, "bad limit");

@@ -73,6 +73,11 @@ DSS_API int dss_profile_read(dss_ctx *ctx, int stage, double *total_ms, int64_t 
  * enable != 0 switches collection on (and zeroes the counters); out may be NULL. Synchronises the device. */
 DSS_API int dss_debug_raster_stats(dss_ctx *ctx, int enable, uint64_t out[8]);
 
+/* Total length of the forward's tile lists as the device published it last (mapped pinned word: no synchronisation, may
+ * lag one call behind).  Lets a caller that replays a captured CUDA graph notice that the lists have outgrown the buffer
+ * the graph was captured with (dss_b200/graph.py). */
+DSS_API int64_t dss_debug_tile_total(const dss_ctx *ctx);
+
 /* Testing: cap the forward's tile-list buffer at max_entries (0 = no cap).  Tiles whose list does not fit are then
  * rasterized from the view's records directly -- the path a sudden growth of the lists takes in production, where the
  * buffer is sized from the previous call without the host ever waiting for the device.  Results must not change. */

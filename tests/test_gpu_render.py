@@ -204,3 +204,38 @@ def test_more_than_256_shared_views_is_refused_before_any_launch(cuda_device):
     with pytest.raises(RuntimeError, match="at most 256 views"):
         render_points(pts.to(d), nrm.to(d), col.to(d), proj.repeat(N, 1, 1).to(d), view.repeat(N, 1, 1).to(d),
                       torch.full((N,), 3e-4, device=d), SplatParams(image_size=32, znear=0.1))
+
+
+def test_graphed_step_replays_the_eager_step(cuda_device):
+    """dss_b200.graph.GraphedRenderStep: forward + backward captured once in a CUDA graph (the library neither
+    synchronises nor allocates in steady state); replays must give the eager results, also after the static inputs
+    were updated in place."""
+    from dss_b200.graph import GraphedRenderStep
+    P0, N, S = 30000, 3, 128
+    pts, nrm, col, proj, view, cams = scene(P0, N, seed=23)
+    d = cuda_device
+    prm = SplatParams(image_size=S, znear=0.1, clip_pts_grad=0.05)
+    h = torch.full((N,), 3e-4, device=d)
+    g = (torch.randn(N, S, S, 4, generator=torch.Generator().manual_seed(8)) * 1e-3).to(d)
+    p = pts.to(d).requires_grad_(True)
+    c = col.to(d).requires_grad_(True)
+    step = GraphedRenderStep(p, nrm.to(d), c, proj.to(d), view.to(d), h, prm, g)
+
+    def eager():
+        pe = p.detach().clone().requires_grad_(True)
+        ce = c.detach().clone().requires_grad_(True)
+        o = render_points(pe, nrm.to(d), ce, proj.to(d), view.to(d), h, prm)
+        o.image.backward(g)
+        return o.image.detach(), pe.grad, ce.grad
+
+    for it in range(3):
+        img = step.replay()
+        torch.cuda.synchronize()
+        wi, wp, wc = eager()
+        assert torch.equal(img, wi)
+        assert torch.equal(step.grad_points, wp)                       # deterministic gather
+        torch.testing.assert_close(step.grad_colours, wc, rtol=1e-4, atol=1e-9)   # float atomics
+        with torch.no_grad():                                          # "optimizer step" on the static tensors
+            p.add_(0.002 * torch.randn(P0, 3, generator=torch.Generator().manual_seed(it)).to(d))
+            c.mul_(0.9)
+    assert not step.stale()
