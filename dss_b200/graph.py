@@ -4,9 +4,13 @@ A step is ~30 kernel launches and two ctypes calls; at the headline size (1.7 ms
 GPU work, at the smaller BASELINE clouds (100k points: 0.6 ms) they do not.  The C library never synchronises or
 allocates in steady state (DESIGN.md "Host side"), so the whole step can be captured once and replayed:
 
-    step = GraphedRenderStep(points, normals, colours, proj, view, h, params, grad_image)   # static tensors
+    step = GraphedRenderStep(points, normals, colours, proj, view, h, params, grad_image)
     step.replay()                    # image in step.image, gradients in step.grad_points / step.grad_colours
-    points.data.add_(...)            # update the static inputs in place (optimizer step), replay again
+    step.points.data.add_(...)       # update the step's OWN static leaves in place (optimizer step), replay again
+
+The step owns its differentiated inputs (`step.points`, `step.colours`, `step.normals`: fresh leaf copies of what was passed
+in): a leaf that has already been through an eager backward on the default stream carries an AccumulateGrad node bound
+to that stream, and synchronising with the legacy default stream is not capturable.
 
 Sizes decided on the host at capture time are frozen into the graph: the forward's tile-list capacity and the staged
 window of the occupancy gather.  Both have on-device fallbacks (tiles whose list outgrew the buffer are rasterized from
@@ -25,13 +29,12 @@ class GraphedRenderStep:
     def __init__(self, points, normals, colours, proj, view, h, params, grad_image, shading=None, warmup=3):
         dev = _lib.require_cuda(points, normals, colours, proj, view, h, grad_image)
         self.device = dev
-        self._args = (points, normals, colours, proj, view, h, params)
+        leaf = lambda t: t.detach().clone().requires_grad_(True)
+        self.points, self.colours = leaf(points), leaf(colours)
+        self.normals = leaf(normals) if shading is not None else normals.detach().clone()
+        self._args = (self.points, self.normals, self.colours, proj, view, h, params)
         self._shading = shading
         self.grad_image = grad_image
-        for t in (points, colours) + ((normals,) if shading is not None else ()):
-            if not t.requires_grad:
-                raise RuntimeError("GraphedRenderStep differentiates its point / colour (/ normal) inputs: "
-                                   "pass leaf tensors with requires_grad=True")
         # warm-up on a side stream (sizes the library's scratch and the caching allocator), then capture
         s = torch.cuda.Stream(device=dev)
         s.wait_stream(torch.cuda.current_stream(dev))
@@ -46,9 +49,8 @@ class GraphedRenderStep:
         with torch.cuda.graph(self.graph):
             out = self._eager()
         self.image, self.visible = out.image, out.visible
-        points, normals, colours = self._args[0], self._args[1], self._args[2]
-        self.grad_points, self.grad_colours = points.grad, colours.grad
-        self.grad_normals = normals.grad if shading is not None else None
+        self.grad_points, self.grad_colours = self.points.grad, self.colours.grad
+        self.grad_normals = self.normals.grad if shading is not None else None
 
     def _clear_grads(self):
         for t in self._args[:3]:

@@ -217,9 +217,13 @@ def test_graphed_step_replays_the_eager_step(cuda_device):
     prm = SplatParams(image_size=S, znear=0.1, clip_pts_grad=0.05)
     h = torch.full((N,), 3e-4, device=d)
     g = (torch.randn(N, S, S, 4, generator=torch.Generator().manual_seed(8)) * 1e-3).to(d)
-    p = pts.to(d).requires_grad_(True)
-    c = col.to(d).requires_grad_(True)
-    step = GraphedRenderStep(p, nrm.to(d), c, proj.to(d), view.to(d), h, prm, g)
+    p0 = pts.to(d).requires_grad_(True)
+    c0 = col.to(d).requires_grad_(True)
+    # leaves that have already been through an eager backward on the default stream (as in a training script that
+    # switches to the graph after a few steps)
+    render_points(p0, nrm.to(d), c0, proj.to(d), view.to(d), h, prm).image.backward(g)
+    step = GraphedRenderStep(p0, nrm.to(d), c0, proj.to(d), view.to(d), h, prm, g)
+    p, c = step.points, step.colours
 
     def eager():
         pe = p.detach().clone().requires_grad_(True)
