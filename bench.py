@@ -354,8 +354,10 @@ def run_ours(a):
             for _ in range(3):
                 graphed.replay()
         except Exception as e:   # pragma: no cover
-            print("CUDA-graph capture failed, timing the eager loop: %r" % (e,), file=sys.stderr)
-            graphed = None
+            # a failed capture can leave the process's CUDA state unusable for timing: start over, eagerly
+            print("CUDA-graph capture failed (%r): re-running with --no-graph" % (e,), file=sys.stderr)
+            sys.stderr.flush()
+            os.execv(sys.executable, [sys.executable] + sys.argv + ["--no-graph"])
     sync_all()
     sampler = ClockSampler(local)
     sampler.start()
