@@ -341,23 +341,34 @@ def run_ours(a):
     launches_per_step = (_lib.launch_count(dev) - launches0) / n_prof
     stages = {k: (v[0] * a.steps / n_prof, v[1]) for k, v in _lib.profile_read(dev).items()}   # scaled to `steps`
     _lib.profile_enable(False, dev)
-    if sync is not None:
-        sync.timings_ms()
+    allreduce = None
+    if sync is not None:      # device time / bytes of the two overlapped collectives, from the same eager pass
+        ar_ms = sync.timings_ms() / n_prof
+        ar_bytes = sync.bytes_reduced / n_prof
+        allreduce = {"ms_per_step": ar_ms, "bytes_per_step": int(ar_bytes), "collectives_per_step": 2,
+                     "busbw_GBs": (2.0 * (world - 1) / world) * ar_bytes / (ar_ms * 1e-3) / 1e9 if ar_ms > 0 else None,
+                     "overlap": "d colour reduced on a side stream during the occupancy gather; d position behind the "
+                                "chain kernel"}
+        sync.timing = False
         sync.reset_counters()
     # ... and the timed region: K steps, replayed from ONE captured CUDA graph of the whole step on a single GPU (the
     # library neither synchronises nor allocates in steady state: dss_b200/graph.py), launched eagerly otherwise
     graphed = None
-    if world == 1 and not a.no_graph:
+    if not a.no_graph and (world == 1 or os.environ.get("BENCH_GRAPH_MULTI", "1") == "1"):
         try:
             from dss_b200.graph import GraphedRenderStep
-            graphed = GraphedRenderStep(pts_d, nrm_d, col_d, proj_d, view_d, h_d, prm, grad_d, shading=shading)
+            graphed = GraphedRenderStep(pts_d, nrm_d, col_d, proj_d, view_d, h_d, prm, grad_d, shading=shading,
+                                        grad_sync=sync)
             for _ in range(3):
                 graphed.replay()
         except Exception as e:   # pragma: no cover
             # a failed capture can leave the process's CUDA state unusable for timing: start over, eagerly
-            print("CUDA-graph capture failed (%r): re-running with --no-graph" % (e,), file=sys.stderr)
+            print("CUDA-graph capture failed (%r): %s" % (e, "re-running with --no-graph" if world == 1 else "eager"),
+                  file=sys.stderr)
             sys.stderr.flush()
-            os.execv(sys.executable, [sys.executable] + sys.argv + ["--no-graph"])
+            if world == 1:
+                os.execv(sys.executable, [sys.executable] + sys.argv + ["--no-graph"])
+            graphed = None
     sync_all()
     sampler = ClockSampler(local)
     sampler.start()
@@ -373,24 +384,6 @@ def run_ours(a):
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
     launches = launches_per_step * a.steps      # kernels executed in the timed region (replayed, not re-launched, under a graph)
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    value = world * V * P0 * a.steps / (ms_max * 1e-3) / 1e6
-    allreduce = None
-    if sync is not None:
-        ar_ms = sync.timings_ms() / a.steps
-        ar_bytes = sync.bytes_reduced / a.steps
-        allreduce = {"ms_per_step": ar_ms, "bytes_per_step": int(ar_bytes), "collectives_per_step": 2,
-                     "busbw_GBs": (2.0 * (world - 1) / world) * ar_bytes / (ar_ms * 1e-3) / 1e9 if ar_ms > 0 else None,
-                     "overlap": "d colour reduced on a side stream during the occupancy gather; d position behind the "
-                                "chain kernel"}
-        sync.timing = False
-    ms = e0.elapsed_time(e1)
-    launches = _lib.launch_count(dev) - launches0
-    stages = _lib.profile_read(dev)
-    _lib.profile_enable(False, dev)
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -26,7 +26,8 @@ __all__ = ["GraphedRenderStep"]
 
 
 class GraphedRenderStep:
-    def __init__(self, points, normals, colours, proj, view, h, params, grad_image, shading=None, warmup=3):
+    def __init__(self, points, normals, colours, proj, view, h, params, grad_image, shading=None, warmup=3,
+                 grad_sync=None):
         dev = _lib.require_cuda(points, normals, colours, proj, view, h, grad_image)
         self.device = dev
         leaf = lambda t: t.detach().clone().requires_grad_(True)
@@ -34,6 +35,7 @@ class GraphedRenderStep:
         self.normals = leaf(normals) if shading is not None else normals.detach().clone()
         self._args = (self.points, self.normals, self.colours, proj, view, h, params)
         self._shading = shading
+        self._sync = grad_sync          # view-sharded step: the overlapped NCCL exchange is captured with the kernels
         self.grad_image = grad_image
         # warm-up on a side stream (sizes the library's scratch and the caching allocator), then capture
         s = torch.cuda.Stream(device=dev)
@@ -46,8 +48,15 @@ class GraphedRenderStep:
         self._capacity_at_capture = self._tile_total()
         self._clear_grads()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            out = self._eager()
+        timing = getattr(grad_sync, "timing", False)
+        if grad_sync is not None:
+            grad_sync.timing = False    # no timing events inside a capture
+        try:
+            with torch.cuda.graph(self.graph):
+                out = self._eager()
+        finally:
+            if grad_sync is not None:
+                grad_sync.timing = timing
         self.image, self.visible = out.image, out.visible
         self.grad_points, self.grad_colours = self.points.grad, self.colours.grad
         self.grad_normals = self.normals.grad if shading is not None else None
@@ -60,7 +69,7 @@ class GraphedRenderStep:
     def _eager(self):
         self._clear_grads()
         points, normals, colours, proj, view, h, params = self._args
-        out = render_points(points, normals, colours, proj, view, h, params, shading=self._shading)
+        out = render_points(points, normals, colours, proj, view, h, params, shading=self._shading, grad_sync=self._sync)
         out.image.backward(self.grad_image)
         return out
 
