@@ -354,11 +354,10 @@ def run_ours(a):
     # ... and the timed region: K steps, replayed from ONE captured CUDA graph of the whole step on a single GPU (the
     # library neither synchronises nor allocates in steady state: dss_b200/graph.py), launched eagerly otherwise
     graphed = None
-    if not a.no_graph and (world == 1 or os.environ.get("BENCH_GRAPH_MULTI", "1") == "1"):
+    if not a.no_graph and world == 1:    # (N > 1 is launched eagerly: the NCCL exchange inside a capture hung on 2 GPUs)
         try:
             from dss_b200.graph import GraphedRenderStep
-            graphed = GraphedRenderStep(pts_d, nrm_d, col_d, proj_d, view_d, h_d, prm, grad_d, shading=shading,
-                                        grad_sync=sync)
+            graphed = GraphedRenderStep(pts_d, nrm_d, col_d, proj_d, view_d, h_d, prm, grad_d, shading=shading)
             for _ in range(3):
                 graphed.replay()
         except Exception as e:   # pragma: no cover

@@ -35,7 +35,12 @@ class GraphedRenderStep:
         self.normals = leaf(normals) if shading is not None else normals.detach().clone()
         self._args = (self.points, self.normals, self.colours, proj, view, h, params)
         self._shading = shading
-        self._sync = grad_sync          # view-sharded step: the overlapped NCCL exchange is captured with the kernels
+        if grad_sync is not None and grad_sync.world_size > 1:
+            # measured on 2 x B200: capturing the two overlapped NCCL all-reduces (issued from two streams inside the
+            # backward) deadlocks at replay -- a view-sharded step is launched eagerly
+            raise NotImplementedError("GraphedRenderStep does not capture the multi-GPU gradient exchange; "
+                                      "call render_points(..., grad_sync=...) eagerly")
+        self._sync = grad_sync
         self.grad_image = grad_image
         # warm-up on a side stream (sizes the library's scratch and the caching allocator), then capture
         s = torch.cuda.Stream(device=dev)
