@@ -98,7 +98,6 @@ struct dss_ctx {
     int raster_stats;   // debug: accumulate raster work counters
     int raster_minb5;   // tuning (env DSS_RASTER_MINB=5): 5 resident CTAs/SM (48 registers) instead of 4 (64)
     int sync_forward;   // tuning (env DSS_SYNC_FORWARD=1): always wait for the tile-list size before the scatter
-    cudaEvent_t ev_total;   // (unused since the forward stopped waiting for the tile-list size)
     int64_t tile_total_hint;   // tile-list size last seen in the mapped word: sizes the key buffer of the next call
     int64_t tile_cap_limit;    // testing (dss_debug_limit_tile_capacity): upper bound on the key buffer, 0 = none
     cudaStream_t side;      // second stream: independent backward work (colour scatter) overlaps the occupancy path

@@ -301,8 +301,7 @@ int dss_create(dss_ctx **out) {
         return DSS_E_NOMEM;
     }
     memset(c->h_pinned, 0, 64 * sizeof(int64_t));
-    if (cudaEventCreateWithFlags(&c->ev_total, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+    if (cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess) {
         cudaGetLastError();
@@ -325,7 +324,6 @@ void dss_destroy(dss_ctx *ctx) {
     for (int i = 0; i < dss::NUM_BUFS; ++i)
         if (ctx->buf[i]) cudaFree(ctx->buf[i]);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
-    if (ctx->ev_total) cudaEventDestroy(ctx->ev_total);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->side) cudaStreamDestroy(ctx->side);
